@@ -1,0 +1,112 @@
+/*
+ * instarevive_b200 -- C ABI of the B200-native (sm_100a) one-step restoration hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only (no torch / C++ types). Every device pointer is
+ * owned by the caller (PyTorch); the library owns only its packed weight copies and small per-handle caches.
+ * Calls are asynchronous on the CUDA stream passed as `stream` (a cudaStream_t cast to void*); they never
+ * synchronise the device. All functions return 0 on success and a non-zero ir_status otherwise, in which case
+ * ir_last_error() describes the failure (the Python host raises RuntimeError, mirroring the reference's
+ * exception-only error convention: assert / raise in diffusion/model/nets/pixart_controlnet.py:172,
+ * scripts/DMD/transformer_train/generate.py:17).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   ir_dit_*          ControlPixArtMSHalf.forward           diffusion/model/nets/pixart_controlnet.py:191-251
+ *                     (PixArtMSBlock.forward                diffusion/model/nets/PixArtMS.py:71-79,
+ *                      AttentionKVCompress / MultiHeadCrossAttention / T2IFinalLayer / embedders
+ *                                                            diffusion/model/nets/PixArt_blocks.py:28-58,123-158,259-463)
+ *   ir_eps_to_x0      eps_to_mu + chunk(2)[0]               scripts/DMD/transformer_train/generate.py:44-51,84-85
+ *   ir_vae_*          AutoencoderKL.decode -> Decoder.forward ldm/models/autoencoder.py:88-91,
+ *                                                            ldm/modules/diffusionmodules/model.py:622-655
+ *   ir_tile_*         tile loops of process()               test_scripts/inference.py:119-153
+ *   ir_wavelet_*      wavelet_reconstruction                utils/image/align_color.py:73-119
+ *   ir_to_uint8       clamp / *255 / uint8 NHWC             test_scripts/inference.py:159-160
+ */
+#ifndef INSTAREVIVE_B200_H_
+#define INSTAREVIVE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ir_status {
+  IR_STATUS_OK = 0,
+  IR_STATUS_INVALID = 1,     /* bad argument / shape */
+  IR_STATUS_CUDA = 2,        /* a CUDA runtime call failed */
+  IR_STATUS_UNSUPPORTED = 3, /* configuration outside what the kernels are specialised for */
+  IR_STATUS_WORKSPACE = 4,   /* caller-provided workspace too small */
+  IR_STATUS_DRIVER = 5       /* driver entry point (tensor-map encode) unavailable */
+} ir_status;
+
+/* Thread-local description of the last failure on this thread; never NULL. */
+const char* ir_last_error(void);
+/* Library version string. */
+const char* ir_version(void);
+/* Kernels launched by this library since load (all threads); bench.py reports the delta as gpu_launches. */
+long long ir_launch_count(void);
+
+/* ------------------------------------------------------------------ DiT + ControlNet-Half ---- */
+typedef struct ir_dit ir_dit; /* opaque: packed weights of one (device, model) */
+
+typedef struct ir_dit_config {
+  int depth;              /* 28 for PixArtMS_XL_2 */
+  int copy_blocks;        /* 13: ControlPixArtMSHalf(copy_blocks_num) */
+  int hidden;             /* 1152 */
+  int heads;              /* 16 */
+  int patch;              /* 2 */
+  int in_channels;        /* 4 */
+  int out_channels;       /* 8 (learned sigma) */
+  int caption_channels;   /* 4096 */
+  int mlp_ratio;          /* 4 */
+  int base_size;          /* input_size // patch_size (PixArt.py:100) */
+  float pe_interpolation; /* PixArt.py:76 */
+} ir_dit_config;
+
+int ir_dit_create(const ir_dit_config* cfg, ir_dit** out);
+void ir_dit_destroy(ir_dit* h);
+/* Parameter table: the names are the reference state_dict keys (SURVEY 8b weight contract). */
+int ir_dit_num_params(const ir_dit* h);
+int ir_dit_param_info(const ir_dit* h, int i, char* name, int name_cap, long long* numel, int* rows, int* cols);
+/* Copy one fp32 parameter (device pointer, reference layout) into the packed device representation. */
+int ir_dit_load_param(ir_dit* h, const char* name, const float* src_dev, long long numel, void* stream);
+size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l);
+/*
+ * x, c: (B,4,H,W) fp32 latents (c may be NULL: plain 28-block path); timestep: (B) fp32;
+ * y: (rows,4096) fp32 caption embeddings; y_index: device int32 (sum_l) valid rows of y, sample-major;
+ * kv_off / kv_len: device int32 (B) offsets / lengths into the packed caption rows;
+ * img_hw: device fp32 (B,2); aspect: device fp32 (B); out: (B,8,H,W) fp32.
+ * reuse_caption != 0 skips the caption embedding and the per-block K/V projections and reuses the ones cached by
+ * the previous call on this handle (same captions, same sum_l).
+ */
+int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* timestep, const float* y,
+                   const int32_t* y_index, const int32_t* kv_off, const int32_t* kv_len, const float* img_hw,
+                   const float* aspect, float* out, int B, int H, int W, int sum_l, int reuse_caption,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* x0 = (x - sqrt(1-abar) * eps) / sqrt(abar); eps = channels [0,C) of model_out (B,2C,H,W). */
+int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
+                 float sqrt_one_minus_abar, void* stream);
+
+/* ------------------------------------------------------------------ unit entry points (parity tests) ---- */
+/* out = epilogue(alpha * A[M,K] * W[N,K]^T + bias). epilogue: 0 bf16, 1 bf16+GELU(tanh), 2 fp32 (+gate, +resid). */
+int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int batch, long long strideA,
+                 long long strideW, long long strideO, int epilogue, float alpha, void* out_bf16, float* out_f32,
+                 const float* resid_f32, const float* gate, long long gate_ld, int rows_per_gate, int force_bn,
+                 void* stream);
+/* 3x3 stride-1 pad-1 convolution on NHWC bf16: act (n,H,W,C), weight (Cout, 9*C) tap-major, out (n,H,W,Cout). */
+int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
+                    void* out_bf16, float* out_f32, const void* resid_bf16, const float* resid_f32, int force_bn,
+                    void* stream);
+int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldk,
+                      long long ldv, long long ldo, int B, int heads, int head_dim, int Tq, int Tk,
+                      const int32_t* kv_off, const int32_t* kv_len, float scale, void* stream);
+int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
+                   int rows, int T, int D, void* stream);
+int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTAREVIVE_B200_H_ */

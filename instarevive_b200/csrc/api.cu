@@ -1,0 +1,228 @@
+// C ABI (include/instarevive_b200.h) over the C++ launchers. No torch types cross this boundary.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/instarevive_b200.h"
+#include "dit.cuh"
+
+namespace ir {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace ir
+
+using namespace ir;
+
+struct ir_dit {
+  Dit* d;
+};
+
+extern "C" {
+
+const char* ir_last_error(void) { return g_err; }
+const char* ir_version(void) { return "instarevive_b200 0.1 (sm_100a)"; }
+long long ir_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ir_dit_create(const ir_dit_config* cfg, ir_dit** out) {
+  if (!cfg || !out) {
+    set_last_error("ir_dit_create: null argument");
+    return IR_ERR_INVALID;
+  }
+  DitConfig c;
+  c.depth = cfg->depth;
+  c.copy_blocks = cfg->copy_blocks;
+  c.hidden = cfg->hidden;
+  c.heads = cfg->heads;
+  c.patch = cfg->patch;
+  c.in_ch = cfg->in_channels;
+  c.out_ch = cfg->out_channels;
+  c.caption_ch = cfg->caption_channels;
+  c.mlp_ratio = cfg->mlp_ratio;
+  c.base_size = cfg->base_size;
+  c.pe_interpolation = cfg->pe_interpolation;
+  Dit* d = nullptr;
+  int st = dit_create(c, &d);
+  if (st != IR_OK) return st;
+  *out = new ir_dit{d};
+  return IR_OK;
+}
+
+void ir_dit_destroy(ir_dit* h) {
+  if (!h) return;
+  dit_destroy(h->d);
+  delete h;
+}
+
+int ir_dit_num_params(const ir_dit* h) { return h ? (int)h->d->params.size() : 0; }
+
+int ir_dit_param_info(const ir_dit* h, int i, char* name, int name_cap, long long* numel, int* rows, int* cols) {
+  if (!h || i < 0 || i >= (int)h->d->params.size()) {
+    set_last_error("ir_dit_param_info: index %d out of range", i);
+    return IR_ERR_INVALID;
+  }
+  const ParamEntry& e = h->d->params[i];
+  if (name && name_cap > 0) {
+    strncpy(name, e.name.c_str(), (size_t)name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (numel) *numel = e.numel;
+  if (rows) *rows = e.rows;
+  if (cols) *cols = e.cols;
+  return IR_OK;
+}
+
+int ir_dit_load_param(ir_dit* h, const char* name, const float* src_dev, long long numel, void* stream) {
+  if (!h || !name || !src_dev) {
+    set_last_error("ir_dit_load_param: null argument");
+    return IR_ERR_INVALID;
+  }
+  return dit_load_param(h->d, name, src_dev, (long)numel, (cudaStream_t)stream);
+}
+
+size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l) {
+  return h ? dit_workspace_bytes(h->d, B, H, W, sum_l) : 0;
+}
+
+int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* timestep, const float* y,
+                   const int32_t* y_index, const int32_t* kv_off, const int32_t* kv_len, const float* img_hw,
+                   const float* aspect, float* out, int B, int H, int W, int sum_l, int reuse_caption,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) {
+    set_last_error("ir_dit_forward: null handle");
+    return IR_ERR_INVALID;
+  }
+  DitForwardArgs a;
+  a.x = x;
+  a.c = c;
+  a.timestep = timestep;
+  a.y = y;
+  a.y_index = y_index;
+  a.kv_off = kv_off;
+  a.kv_len = kv_len;
+  a.img_hw = img_hw;
+  a.aspect = aspect;
+  a.out = out;
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  a.sumL = sum_l;
+  a.reuse_caption = reuse_caption;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace_bytes;
+  return dit_forward(h->d, a, (cudaStream_t)stream);
+}
+
+int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
+                 float sqrt_one_minus_abar, void* stream) {
+  return eps_to_x0_launch(x, model_out, x0, B, C, HW, sqrt_abar, sqrt_one_minus_abar, (cudaStream_t)stream);
+}
+
+int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int batch, long long strideA,
+                 long long strideW, long long strideO, int epilogue, float alpha, void* out_bf16, float* out_f32,
+                 const float* resid_f32, const float* gate, long long gate_ld, int rows_per_gate, int force_bn,
+                 void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)A;
+  g.lda = K;
+  g.strideA = strideA;
+  g.W = (const bf16*)W;
+  g.ldw = K;
+  g.strideW = strideW;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.batch = batch;
+  g.epi = epilogue;
+  g.alpha = alpha;
+  g.bias = bias;
+  g.out_bf16 = (bf16*)out_bf16;
+  g.ldo_b = N;
+  g.stride_ob = strideO;
+  g.out_f32 = out_f32;
+  g.resid_f32 = resid_f32;
+  g.ldo_f = N;
+  g.stride_of = strideO;
+  g.gate = gate;
+  g.gate_ld = gate_ld;
+  g.rows_per_gate = rows_per_gate;
+  g.force_bn = force_bn;
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
+int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
+                    void* out_bf16, float* out_f32, const void* resid_bf16, const float* resid_f32, int force_bn,
+                    void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)act;
+  g.W = (const bf16*)weight;
+  g.ldw = 9L * C;
+  g.M = n * H * W;
+  g.N = Cout;
+  g.K = 9 * C;
+  g.conv = 1;
+  g.nimg = n;
+  g.H = H;
+  g.Wd = W;
+  g.C = C;
+  g.bias = bias;
+  g.force_bn = force_bn;
+  if (out_f32) {
+    g.epi = EPI_F32;
+    g.out_f32 = out_f32;
+    g.resid_f32 = resid_f32;
+    g.ldo_f = Cout;
+    g.out_bf16 = (bf16*)out_bf16;
+    g.ldo_b = Cout;
+  } else {
+    g.epi = EPI_BF16;
+    g.out_bf16 = (bf16*)out_bf16;
+    g.resid_bf16 = (const bf16*)resid_bf16;
+    g.ldo_b = Cout;
+  }
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
+int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldk,
+                      long long ldv, long long ldo, int B, int heads, int head_dim, int Tq, int Tk,
+                      const int32_t* kv_off, const int32_t* kv_len, float scale, void* stream) {
+  AttnArgs a;
+  a.q = (const bf16*)q;
+  a.k = (const bf16*)k;
+  a.v = (const bf16*)v;
+  a.out = (bf16*)out;
+  a.ldq = ldq;
+  a.ldk = ldk;
+  a.ldv = ldv;
+  a.ldo = ldo;
+  a.B = B;
+  a.heads = heads;
+  a.head_dim = head_dim;
+  a.Tq = Tq;
+  a.Tk = Tk;
+  a.kv_off = kv_off;
+  a.kv_len = kv_len;
+  a.scale = scale;
+  return attention_launch(a, (cudaStream_t)stream);
+}
+
+int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
+                   int rows, int T, int D, void* stream) {
+  return ln_modulate_launch(x, (bf16*)out_bf16, shift, scale, mod_stride, rows, T, D, (cudaStream_t)stream);
+}
+
+int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream) {
+  return pos_embed_launch(table, gh, gw, D, base_size, pe_interpolation, (cudaStream_t)stream);
+}
+
+}  // extern "C"

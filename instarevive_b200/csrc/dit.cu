@@ -1,0 +1,475 @@
+// DiT + ControlNet-Half forward (ControlPixArtMSHalf.forward, diffusion/model/nets/pixart_controlnet.py:191-251)
+// as a stream-ordered schedule of the sm_100a kernels in gemm.cu / attention.cu / elementwise.cu.
+// Precision plan: bf16 MMA operands, fp32 accumulation, fp32 residual streams, fp32 LayerNorm / softmax / adaLN.
+#include "dit.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace ir {
+
+// ------------------------------------------------------------------------------------------------ parameters
+static long align_up(long v, long a) { return (v + a - 1) / a * a; }
+
+static void add_param(Dit* d, const std::string& name, int kind, int rows, int cols) {
+  ParamEntry e;
+  e.name = name;
+  e.kind = kind;
+  e.rows = rows;
+  e.cols = cols;
+  e.numel = (long)rows * cols;
+  if (kind == PK_BF16) {
+    e.offset = d->wb_elems;
+    d->wb_elems = align_up(d->wb_elems + e.numel, 64);
+  } else {
+    e.offset = d->wf_elems;
+    d->wf_elems = align_up(d->wf_elems + e.numel, 64);
+  }
+  d->index[name] = (int)d->params.size();
+  d->params.push_back(e);
+}
+
+static std::string block_prefix(const Dit* d, int blk) {
+  if (blk < d->cfg.depth) return "base_model.blocks." + std::to_string(blk);
+  return "controlnet." + std::to_string(blk - d->cfg.depth) + ".copied_block";
+}
+
+template <typename T>
+static const T* pptr(const Dit* d, const std::string& name) {
+  auto it = d->index.find(name);
+  if (it == d->index.end()) return nullptr;
+  const ParamEntry& e = d->params[it->second];
+  if (e.kind == PK_BF16) return reinterpret_cast<const T*>(d->wb + e.offset);
+  return reinterpret_cast<const T*>(d->wf + e.offset);
+}
+
+int dit_create(const DitConfig& cfg, Dit** out) {
+  IR_REQUIRE(cfg.hidden == 1152 && cfg.heads == 16, "dit: kernels are specialised for hidden 1152 / 16 heads (XL/2)");
+  IR_REQUIRE(cfg.patch == 2 && cfg.out_ch == 8 && cfg.in_ch == 4, "dit: patch 2, 4 latent channels, 8 outputs expected");
+  IR_REQUIRE(cfg.copy_blocks >= 0 && cfg.copy_blocks < cfg.depth, "dit: copy_blocks must be in [0, depth)");
+  Dit* d = new Dit();
+  d->cfg = cfg;
+  d->nblk = cfg.depth + cfg.copy_blocks;
+  const int D = cfg.hidden, Dm = cfg.hidden * cfg.mlp_ratio, Dz = cfg.hidden / 3;
+
+  // contiguous regions first: adaLN tables, caption K/V projections (one batched GEMM over all blocks)
+  for (int b = 0; b < d->nblk; ++b) add_param(d, block_prefix(d, b) + ".scale_shift_table", PK_F32, 6, D);
+  for (int b = 0; b < d->nblk; ++b) add_param(d, block_prefix(d, b) + ".cross_attn.kv_linear.weight", PK_BF16, 2 * D, D);
+  for (int b = 0; b < d->nblk; ++b) add_param(d, block_prefix(d, b) + ".cross_attn.kv_linear.bias", PK_F32, 2 * D, 1);
+  for (int b = 0; b < d->nblk; ++b) {
+    const std::string p = block_prefix(d, b);
+    add_param(d, p + ".attn.qkv.weight", PK_BF16, 3 * D, D);
+    add_param(d, p + ".attn.qkv.bias", PK_F32, 3 * D, 1);
+    add_param(d, p + ".attn.proj.weight", PK_BF16, D, D);
+    add_param(d, p + ".attn.proj.bias", PK_F32, D, 1);
+    add_param(d, p + ".cross_attn.q_linear.weight", PK_BF16, D, D);
+    add_param(d, p + ".cross_attn.q_linear.bias", PK_F32, D, 1);
+    add_param(d, p + ".cross_attn.proj.weight", PK_BF16, D, D);
+    add_param(d, p + ".cross_attn.proj.bias", PK_F32, D, 1);
+    add_param(d, p + ".mlp.fc1.weight", PK_BF16, Dm, D);
+    add_param(d, p + ".mlp.fc1.bias", PK_F32, Dm, 1);
+    add_param(d, p + ".mlp.fc2.weight", PK_BF16, D, Dm);
+    add_param(d, p + ".mlp.fc2.bias", PK_F32, D, 1);
+  }
+  if (cfg.copy_blocks > 0) {
+    add_param(d, "controlnet.0.before_proj.weight", PK_BF16, D, D);
+    add_param(d, "controlnet.0.before_proj.bias", PK_F32, D, 1);
+  }
+  for (int j = 0; j < cfg.copy_blocks; ++j) {
+    add_param(d, "controlnet." + std::to_string(j) + ".after_proj.weight", PK_BF16, D, D);
+    add_param(d, "controlnet." + std::to_string(j) + ".after_proj.bias", PK_F32, D, 1);
+  }
+  const std::string bm = "base_model.";
+  add_param(d, bm + "x_embedder.proj.weight", PK_F32_TRANSPOSED, D, cfg.in_ch * 4);
+  add_param(d, bm + "x_embedder.proj.bias", PK_F32, D, 1);
+  add_param(d, bm + "t_embedder.mlp.0.weight", PK_F32, D, 256);
+  add_param(d, bm + "t_embedder.mlp.0.bias", PK_F32, D, 1);
+  add_param(d, bm + "t_embedder.mlp.2.weight", PK_F32, D, D);
+  add_param(d, bm + "t_embedder.mlp.2.bias", PK_F32, D, 1);
+  const char* sz[2] = {"csize_embedder", "ar_embedder"};
+  for (int i = 0; i < 2; ++i) {
+    add_param(d, bm + sz[i] + ".mlp.0.weight", PK_F32, Dz, 256);
+    add_param(d, bm + sz[i] + ".mlp.0.bias", PK_F32, Dz, 1);
+    add_param(d, bm + sz[i] + ".mlp.2.weight", PK_F32, Dz, Dz);
+    add_param(d, bm + sz[i] + ".mlp.2.bias", PK_F32, Dz, 1);
+  }
+  add_param(d, bm + "t_block.1.weight", PK_F32, 6 * D, D);
+  add_param(d, bm + "t_block.1.bias", PK_F32, 6 * D, 1);
+  add_param(d, bm + "y_embedder.y_proj.fc1.weight", PK_BF16, D, cfg.caption_ch);
+  add_param(d, bm + "y_embedder.y_proj.fc1.bias", PK_F32, D, 1);
+  add_param(d, bm + "y_embedder.y_proj.fc2.weight", PK_BF16, D, D);
+  add_param(d, bm + "y_embedder.y_proj.fc2.bias", PK_F32, D, 1);
+  add_param(d, bm + "final_layer.scale_shift_table", PK_F32, 2, D);
+  add_param(d, bm + "final_layer.linear.weight", PK_F32, cfg.patch * cfg.patch * cfg.out_ch, D);
+  add_param(d, bm + "final_layer.linear.bias", PK_F32, cfg.patch * cfg.patch * cfg.out_ch, 1);
+
+  if (cudaMalloc(&d->wb, (size_t)d->wb_elems * sizeof(bf16)) != cudaSuccess ||
+      cudaMalloc(&d->wf, (size_t)d->wf_elems * sizeof(float)) != cudaSuccess) {
+    set_last_error("dit_create: cudaMalloc of %.1f MB weights failed: %s",
+                   (d->wb_elems * 2.0 + d->wf_elems * 4.0) / 1e6, cudaGetErrorString(cudaGetLastError()));
+    dit_destroy(d);
+    return IR_ERR_CUDA;
+  }
+
+  d->blocks.resize(d->nblk);
+  for (int b = 0; b < d->nblk; ++b) {
+    const std::string p = block_prefix(d, b);
+    BlockW& w = d->blocks[b];
+    w.qkv = pptr<bf16>(d, p + ".attn.qkv.weight");
+    w.b_qkv = pptr<float>(d, p + ".attn.qkv.bias");
+    w.proj = pptr<bf16>(d, p + ".attn.proj.weight");
+    w.b_proj = pptr<float>(d, p + ".attn.proj.bias");
+    w.q_lin = pptr<bf16>(d, p + ".cross_attn.q_linear.weight");
+    w.b_q = pptr<float>(d, p + ".cross_attn.q_linear.bias");
+    w.b_kv = pptr<float>(d, p + ".cross_attn.kv_linear.bias");
+    w.cproj = pptr<bf16>(d, p + ".cross_attn.proj.weight");
+    w.b_cproj = pptr<float>(d, p + ".cross_attn.proj.bias");
+    w.fc1 = pptr<bf16>(d, p + ".mlp.fc1.weight");
+    w.b_fc1 = pptr<float>(d, p + ".mlp.fc1.bias");
+    w.fc2 = pptr<bf16>(d, p + ".mlp.fc2.weight");
+    w.b_fc2 = pptr<float>(d, p + ".mlp.fc2.bias");
+  }
+  d->tables = pptr<float>(d, block_prefix(d, 0) + ".scale_shift_table");
+  d->kv_all = pptr<bf16>(d, block_prefix(d, 0) + ".cross_attn.kv_linear.weight");
+  d->b_kv_all = pptr<float>(d, block_prefix(d, 0) + ".cross_attn.kv_linear.bias");
+  d->before_proj = pptr<bf16>(d, "controlnet.0.before_proj.weight");
+  d->b_before = pptr<float>(d, "controlnet.0.before_proj.bias");
+  for (int j = 0; j < cfg.copy_blocks; ++j) {
+    d->after_proj.push_back(pptr<bf16>(d, "controlnet." + std::to_string(j) + ".after_proj.weight"));
+    d->b_after.push_back(pptr<float>(d, "controlnet." + std::to_string(j) + ".after_proj.bias"));
+  }
+  d->xw_t = pptr<float>(d, bm + "x_embedder.proj.weight");
+  d->xb = pptr<float>(d, bm + "x_embedder.proj.bias");
+  d->t_w0 = pptr<float>(d, bm + "t_embedder.mlp.0.weight");
+  d->t_b0 = pptr<float>(d, bm + "t_embedder.mlp.0.bias");
+  d->t_w2 = pptr<float>(d, bm + "t_embedder.mlp.2.weight");
+  d->t_b2 = pptr<float>(d, bm + "t_embedder.mlp.2.bias");
+  d->cs_w0 = pptr<float>(d, bm + "csize_embedder.mlp.0.weight");
+  d->cs_b0 = pptr<float>(d, bm + "csize_embedder.mlp.0.bias");
+  d->cs_w2 = pptr<float>(d, bm + "csize_embedder.mlp.2.weight");
+  d->cs_b2 = pptr<float>(d, bm + "csize_embedder.mlp.2.bias");
+  d->ar_w0 = pptr<float>(d, bm + "ar_embedder.mlp.0.weight");
+  d->ar_b0 = pptr<float>(d, bm + "ar_embedder.mlp.0.bias");
+  d->ar_w2 = pptr<float>(d, bm + "ar_embedder.mlp.2.weight");
+  d->ar_b2 = pptr<float>(d, bm + "ar_embedder.mlp.2.bias");
+  d->tb_w = pptr<float>(d, bm + "t_block.1.weight");
+  d->tb_b = pptr<float>(d, bm + "t_block.1.bias");
+  d->y_fc1 = pptr<bf16>(d, bm + "y_embedder.y_proj.fc1.weight");
+  d->y_b1 = pptr<float>(d, bm + "y_embedder.y_proj.fc1.bias");
+  d->y_fc2 = pptr<bf16>(d, bm + "y_embedder.y_proj.fc2.weight");
+  d->y_b2 = pptr<float>(d, bm + "y_embedder.y_proj.fc2.bias");
+  d->fin_table = pptr<float>(d, bm + "final_layer.scale_shift_table");
+  d->fin_w = pptr<float>(d, bm + "final_layer.linear.weight");
+  d->fin_b = pptr<float>(d, bm + "final_layer.linear.bias");
+  *out = d;
+  return IR_OK;
+}
+
+void dit_destroy(Dit* d) {
+  if (!d) return;
+  cudaFree(d->wb);
+  cudaFree(d->wf);
+  cudaFree(d->pos);
+  cudaFree(d->ykv);
+  delete d;
+}
+
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const long total = (long)rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(long)c * rows + r] = src[i];
+  }
+}
+
+int dit_load_param(Dit* d, const char* name, const float* src_dev, long numel, cudaStream_t s) {
+  auto it = d->index.find(name);
+  if (it == d->index.end()) {
+    set_last_error("dit_load_param: unknown parameter '%s'", name);
+    return IR_ERR_INVALID;
+  }
+  ParamEntry& e = d->params[it->second];
+  IR_REQUIRE(numel == e.numel, "dit_load_param: '%s' has %ld elements, expected %ld", name, numel, e.numel);
+  if (e.kind == PK_BF16) {
+    IR_TRY(f32_to_bf16_launch(src_dev, d->wb + e.offset, numel, s));
+  } else if (e.kind == PK_F32) {
+    IR_CUDA_CHECK(cudaMemcpyAsync(d->wf + e.offset, src_dev, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    transpose_f32_kernel<<<(int)((numel + 255) / 256), 256, 0, s>>>(src_dev, d->wf + e.offset, e.rows, e.cols);
+    IR_CUDA_CHECK(cudaGetLastError());
+  }
+  e.loaded = true;
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct DitWs {
+  float *xs, *cs;                 // fp32 residual streams (base, control)
+  bf16 *xq, *cb;                  // bf16 copies (cross-attn query input / control stream for after_proj)
+  bf16 *xn, *qkv, *att, *qc, *hm; // per-block scratch
+  bf16* ctok;                     // patch-embedded control tokens (bf16, before_proj input)
+  float *sin, *hid, *t, *t0, *mod;
+  bf16 *yg, *yh, *ye;
+};
+
+static size_t carve(const Dit* d, DitWs& w, void* base, int B, int H, int W, int sumL) {
+  const long D = d->cfg.hidden, Dm = D * d->cfg.mlp_ratio;
+  const long M = (long)B * (H / 2) * (W / 2);
+  Bump b(base);
+  w.xs = b.take<float>(M * D);
+  w.cs = b.take<float>(M * D);
+  w.xq = b.take<bf16>(M * D);
+  w.cb = b.take<bf16>(M * D);
+  w.ctok = b.take<bf16>(M * D);
+  w.xn = b.take<bf16>(M * D);
+  w.qkv = b.take<bf16>(M * 3 * D);
+  w.att = b.take<bf16>(M * D);
+  w.qc = b.take<bf16>(M * D);
+  w.hm = b.take<bf16>(M * Dm);
+  w.sin = b.take<float>((long)B * 4 * 256);
+  w.hid = b.take<float>((long)B * 4 * D);
+  w.t = b.take<float>((long)B * D);
+  w.t0 = b.take<float>((long)B * 6 * D);
+  w.mod = b.take<float>((long)d->nblk * B * 6 * D);
+  const long L = sumL > 0 ? sumL : 1;
+  w.yg = b.take<bf16>(L * d->cfg.caption_ch);
+  w.yh = b.take<bf16>(L * D);
+  w.ye = b.take<bf16>(L * D);
+  return (b.off + 255) & ~size_t(255);
+}
+
+size_t dit_workspace_bytes(const Dit* d, int B, int H, int W, int sumL) {
+  DitWs w;
+  return carve(d, w, nullptr, B, H, W, sumL);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+struct Ctx {
+  Dit* d;
+  DitWs w;
+  int B, T, M, sumL;
+  const int *kv_off, *kv_len;
+  cudaStream_t s;
+};
+
+// gather the 4 scalars per sample that feed the sinusoid embedders: [t, h, w, ar]
+__global__ void cond_scalars_kernel(const float* __restrict__ t, const float* __restrict__ hw,
+                                    const float* __restrict__ ar, float* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  out[b] = t[b];
+  out[B + 2 * b] = hw[2 * b];
+  out[B + 2 * b + 1] = hw[2 * b + 1];
+  out[3 * B + b] = ar[b];
+}
+
+// one PixArtMSBlock (PixArtMS.py:71-79) on the fp32 stream xs; bf16_copy (optional) receives bf16(xs) at the end
+static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
+  Dit* d = c.d;
+  const BlockW& w = d->blocks[blk];
+  const int D = d->cfg.hidden, Dm = D * d->cfg.mlp_ratio, M = c.M, T = c.T;
+  const float* mod = c.w.mod + (long)blk * c.B * 6 * D;  // [B][6][D]: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+  const float attn_scale = 1.0f / sqrtf((float)(D / d->cfg.heads));
+
+  // x = x + gate_msa * attn(modulate(norm1(x)))
+  IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 0 * D, mod + 1 * D, 6 * D, M, T, D, c.s));
+  {
+    GemmArgs g;
+    g.A = c.w.xn; g.lda = D; g.W = w.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+    g.epi = EPI_BF16; g.bias = w.b_qkv; g.out_bf16 = c.w.qkv; g.ldo_b = 3 * D;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  {
+    AttnArgs a;
+    a.q = c.w.qkv; a.k = c.w.qkv + D; a.v = c.w.qkv + 2 * D; a.out = c.w.att;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.B = c.B; a.heads = d->cfg.heads; a.head_dim = D / d->cfg.heads; a.Tq = T; a.Tk = T; a.scale = attn_scale;
+    IR_TRY(attention_launch(a, c.s));
+  }
+  {
+    GemmArgs g;
+    g.A = c.w.att; g.lda = D; g.W = w.proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_F32; g.bias = w.b_proj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    g.gate = mod + 2 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
+    g.out_bf16 = c.w.xq; g.ldo_b = D;  // bf16(x) feeds the cross-attention query projection
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  // x = x + cross_attn(x, y, mask)
+  {
+    GemmArgs g;
+    g.A = c.w.xq; g.lda = D; g.W = w.q_lin; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_BF16; g.bias = w.b_q; g.out_bf16 = c.w.qc; g.ldo_b = D;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  {
+    const bf16* kv = d->ykv + (long)blk * c.sumL * 2 * D;
+    AttnArgs a;
+    a.q = c.w.qc; a.k = kv; a.v = kv + D; a.out = c.w.att;
+    a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
+    a.B = c.B; a.heads = d->cfg.heads; a.head_dim = D / d->cfg.heads; a.Tq = T; a.Tk = 0;
+    a.kv_off = c.kv_off; a.kv_len = c.kv_len; a.scale = attn_scale;
+    IR_TRY(attention_launch(a, c.s));
+  }
+  {
+    GemmArgs g;
+    g.A = c.w.att; g.lda = D; g.W = w.cproj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_F32; g.bias = w.b_cproj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  // x = x + gate_mlp * mlp(modulate(norm2(x)))
+  IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 3 * D, mod + 4 * D, 6 * D, M, T, D, c.s));
+  {
+    GemmArgs g;
+    g.A = c.w.xn; g.lda = D; g.W = w.fc1; g.ldw = D; g.M = M; g.N = Dm; g.K = D;
+    g.epi = EPI_BF16_GELU; g.bias = w.b_fc1; g.out_bf16 = c.w.hm; g.ldo_b = Dm;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  {
+    GemmArgs g;
+    g.A = c.w.hm; g.lda = Dm; g.W = w.fc2; g.ldw = Dm; g.M = M; g.N = D; g.K = Dm;
+    g.epi = EPI_F32; g.bias = w.b_fc2; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    g.gate = mod + 5 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
+    g.out_bf16 = bf16_copy; g.ldo_b = D;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  return IR_OK;
+}
+
+int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
+  IR_REQUIRE(a.x && a.timestep && a.out && a.img_hw && a.aspect, "dit_forward: null input");
+  IR_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.H % 2 == 0 && a.W % 2 == 0, "dit_forward: bad latent shape %dx%dx%d",
+             a.B, a.H, a.W);
+  IR_REQUIRE(a.sumL > 0 && a.kv_off && a.kv_len, "dit_forward: caption token table missing");
+  IR_REQUIRE(!a.c || d->cfg.copy_blocks > 0, "dit_forward: control input given but the model has no control blocks");
+  for (const ParamEntry& e : d->params)
+    IR_REQUIRE(e.loaded, "dit_forward: parameter '%s' was never loaded", e.name.c_str());
+  const size_t need = dit_workspace_bytes(d, a.B, a.H, a.W, a.sumL);
+  if (!a.workspace || a.workspace_bytes < need) {
+    set_last_error("dit_forward: workspace too small (%zu < %zu bytes)", a.workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  IR_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0, "dit_forward: workspace must be 256-byte aligned");
+
+  Ctx c;
+  c.d = d;
+  c.s = s;
+  c.B = a.B;
+  const int gh = a.H / 2, gw = a.W / 2;
+  c.T = gh * gw;
+  c.M = a.B * c.T;
+  c.sumL = a.sumL;
+  c.kv_off = a.kv_off;
+  c.kv_len = a.kv_len;
+  carve(d, c.w, a.workspace, a.B, a.H, a.W, a.sumL);
+  const int D = d->cfg.hidden, B = a.B;
+
+  // ---- position table (cached per token grid; reference recomputes it on the host every call)
+  if (d->pos_gh != gh || d->pos_gw != gw) {
+    if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
+    d->pos = nullptr;
+    IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)c.T * D * sizeof(float)));
+    d->pos_gh = gh;
+    d->pos_gw = gw;
+    IR_TRY(pos_embed_launch(d->pos, gh, gw, D, d->cfg.base_size, d->cfg.pe_interpolation, s));
+  }
+
+  // ---- conditioning: t = t_embedder(timestep) + cat(csize_embedder(img_hw), ar_embedder(ar)); t0 = t_block(t)
+  {
+    const int Dz = D / 3;
+    cond_scalars_kernel<<<(B + 127) / 128, 128, 0, s>>>(a.timestep, a.img_hw, a.aspect, c.w.hid, B);
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    float* scal = c.w.hid;            // [4B] scalars, reused below after the sinusoid pass
+    IR_TRY(sinusoid_launch(scal, c.w.sin, 4 * B, s));  // rows: [0,B) t, [B,3B) (h,w) pairs, [3B,4B) ar
+    float* h_t = c.w.hid;             // [B][D]
+    float* h_cs = c.w.hid + (long)B * D;            // [2B][Dz]
+    float* h_ar = h_cs + (long)2 * B * Dz;          // [B][Dz]
+    IR_TRY(small_linear_launch(c.w.sin, 256, d->t_w0, d->t_b0, h_t, D, 1, D, B, D, 256, ACT_NONE, ACT_SILU, 0, s));
+    IR_TRY(small_linear_launch(c.w.sin + (long)B * 256, 256, d->cs_w0, d->cs_b0, h_cs, Dz, 1, Dz, 2 * B, Dz, 256,
+                               ACT_NONE, ACT_SILU, 0, s));
+    IR_TRY(small_linear_launch(c.w.sin + (long)3 * B * 256, 256, d->ar_w0, d->ar_b0, h_ar, Dz, 1, Dz, B, Dz, 256,
+                               ACT_NONE, ACT_SILU, 0, s));
+    IR_TRY(small_linear_launch(h_t, D, d->t_w2, d->t_b2, c.w.t, D, 1, D, B, D, D, ACT_NONE, ACT_NONE, 0, s));
+    // csize rows (b, dim) land at t[b][dim*Dz : (dim+1)*Dz], the aspect-ratio row at t[b][2*Dz : 3*Dz]
+    IR_TRY(small_linear_launch(h_cs, Dz, d->cs_w2, d->cs_b2, c.w.t, Dz, 2, D, 2 * B, Dz, Dz, ACT_NONE, ACT_NONE, 1, s));
+    IR_TRY(small_linear_launch(h_ar, Dz, d->ar_w2, d->ar_b2, c.w.t + 2 * Dz, Dz, 1, D, B, Dz, Dz, ACT_NONE, ACT_NONE, 1, s));
+    IR_TRY(small_linear_launch(c.w.t, D, d->tb_w, d->tb_b, c.w.t0, 6 * D, 1, 6 * D, B, 6 * D, D, ACT_SILU, ACT_NONE, 0, s));
+    IR_TRY(adaln_table_launch(d->tables, c.w.t0, c.w.mod, d->nblk, B, D, s));
+  }
+
+  // ---- caption: y_embedder on the valid tokens, then K/V projections of all blocks in one batched GEMM
+  if (!a.reuse_caption || d->ykv_sumL != a.sumL) {
+    IR_REQUIRE(a.y && a.y_index, "dit_forward: caption embeddings missing");
+    const long need_kv = (long)d->nblk * a.sumL * 2 * D;
+    if (need_kv > d->ykv_cap) {
+      if (d->ykv) IR_CUDA_CHECK(cudaFree(d->ykv));
+      d->ykv = nullptr;
+      d->ykv_cap = 0;
+      IR_CUDA_CHECK(cudaMalloc(&d->ykv, (size_t)need_kv * sizeof(bf16)));
+      d->ykv_cap = need_kv;
+    }
+    IR_TRY(gather_rows_launch(a.y, a.y_index, c.w.yg, a.sumL, d->cfg.caption_ch, s));
+    GemmArgs g1;
+    g1.A = c.w.yg; g1.lda = d->cfg.caption_ch; g1.W = d->y_fc1; g1.ldw = d->cfg.caption_ch;
+    g1.M = a.sumL; g1.N = D; g1.K = d->cfg.caption_ch;
+    g1.epi = EPI_BF16_GELU; g1.bias = d->y_b1; g1.out_bf16 = c.w.yh; g1.ldo_b = D;
+    IR_TRY(gemm_launch(g1, s));
+    GemmArgs g2;
+    g2.A = c.w.yh; g2.lda = D; g2.W = d->y_fc2; g2.ldw = D; g2.M = a.sumL; g2.N = D; g2.K = D;
+    g2.epi = EPI_BF16; g2.bias = d->y_b2; g2.out_bf16 = c.w.ye; g2.ldo_b = D;
+    IR_TRY(gemm_launch(g2, s));
+    GemmArgs g3;
+    g3.A = c.w.ye; g3.lda = D; g3.strideA = 0;
+    g3.W = d->kv_all; g3.ldw = D; g3.strideW = (long)2 * D * D;
+    g3.M = a.sumL; g3.N = 2 * D; g3.K = D; g3.batch = d->nblk;
+    g3.epi = EPI_BF16; g3.bias = d->b_kv_all; g3.stride_bias = 2 * D;
+    g3.out_bf16 = d->ykv; g3.ldo_b = 2 * D; g3.stride_ob = (long)a.sumL * 2 * D;
+    IR_TRY(gemm_launch(g3, s));
+    d->ykv_sumL = a.sumL;
+  }
+
+  // ---- tokens
+  IR_TRY(patch_embed_launch(a.x, d->xw_t, d->xb, d->pos, c.w.xs, nullptr, B, d->cfg.in_ch, a.H, a.W, D, s));
+  if (a.c) IR_TRY(patch_embed_launch(a.c, d->xw_t, d->xb, d->pos, nullptr, c.w.ctok, B, d->cfg.in_ch, a.H, a.W, D, s));
+
+  // ---- blocks (pixart_controlnet.py:234-247)
+  IR_TRY(run_block(c, 0, c.w.xs, nullptr));
+  int next = 1;
+  if (a.c) {
+    // controlnet[0]: c = before_proj(c); c = copied_block(x + c)
+    GemmArgs g;
+    g.A = c.w.ctok; g.lda = D; g.W = d->before_proj; g.ldw = D; g.M = c.M; g.N = D; g.K = D;
+    g.epi = EPI_F32; g.bias = d->b_before; g.out_f32 = c.w.cs; g.resid_f32 = c.w.xs; g.ldo_f = D;
+    IR_TRY(gemm_launch(g, s));
+    for (int i = 1; i <= d->cfg.copy_blocks; ++i) {
+      IR_TRY(run_block(c, d->cfg.depth + i - 1, c.w.cs, c.w.cb));
+      // x = x + after_proj(c)
+      GemmArgs ga;
+      ga.A = c.w.cb; ga.lda = D; ga.W = d->after_proj[i - 1]; ga.ldw = D; ga.M = c.M; ga.N = D; ga.K = D;
+      ga.epi = EPI_F32; ga.bias = d->b_after[i - 1]; ga.out_f32 = c.w.xs; ga.resid_f32 = c.w.xs; ga.ldo_f = D;
+      IR_TRY(gemm_launch(ga, s));
+      IR_TRY(run_block(c, i, c.w.xs, nullptr));
+    }
+    next = d->cfg.copy_blocks + 1;
+  }
+  for (int i = next; i < d->cfg.depth; ++i) IR_TRY(run_block(c, i, c.w.xs, nullptr));
+
+  // ---- final layer + unpatchify
+  IR_TRY(final_layer_launch(c.w.xs, d->fin_table, c.w.t, d->fin_w, d->fin_b, a.out, B, gh, gw, D, d->cfg.out_ch, s));
+  return IR_OK;
+}
+
+}  // namespace ir

@@ -1,0 +1,101 @@
+// DiT + ControlNet-Half model handle: packed weights on the device and the forward schedule (dit.cu).
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+
+namespace ir {
+
+struct DitConfig {
+  int depth = 28;           // PixArtMS_XL_2: PixArtMS.py:291-293
+  int copy_blocks = 13;     // ControlPixArtMSHalf default, pixart_controlnet.py:188
+  int hidden = 1152;
+  int heads = 16;
+  int patch = 2;
+  int in_ch = 4;
+  int out_ch = 8;           // learn_sigma / pred_sigma: 2 * in_ch
+  int caption_ch = 4096;
+  int mlp_ratio = 4;
+  int base_size = 32;       // input_size // patch_size, PixArt.py:100
+  float pe_interpolation = 1.0f;
+};
+
+enum ParamKind { PK_BF16 = 0, PK_F32 = 1, PK_F32_TRANSPOSED = 2 };
+
+struct ParamEntry {
+  std::string name;   // reference state_dict key
+  int kind;
+  long numel;
+  int rows, cols;     // logical (out, in) shape for matrices; rows = numel, cols = 1 for vectors
+  long offset;        // element offset into the bf16 or fp32 blob
+  bool loaded = false;
+};
+
+struct BlockW {
+  const bf16 *qkv, *proj, *q_lin, *cproj, *fc1, *fc2;
+  const float *b_qkv, *b_proj, *b_q, *b_kv, *b_cproj, *b_fc1, *b_fc2;
+};
+
+struct Dit {
+  DitConfig cfg;
+  int nblk = 0;  // depth + copy_blocks
+  std::vector<ParamEntry> params;
+  std::unordered_map<std::string, int> index;
+  bf16* wb = nullptr;   // bf16 blob
+  float* wf = nullptr;  // fp32 blob
+  long wb_elems = 0, wf_elems = 0;
+
+  // resolved pointers
+  std::vector<BlockW> blocks;      // [depth] base, then [copy_blocks] control
+  const bf16* kv_all = nullptr;    // [nblk][2D][D]
+  const float* b_kv_all = nullptr; // [nblk][2D]
+  const float* tables = nullptr;   // [nblk][6][D]
+  const bf16* before_proj = nullptr;
+  const float* b_before = nullptr;
+  std::vector<const bf16*> after_proj;
+  std::vector<const float*> b_after;
+  const float *xw_t, *xb;                      // x_embedder (transposed [C*4][D]) and bias
+  const float *t_w0, *t_b0, *t_w2, *t_b2;      // t_embedder.mlp
+  const float *cs_w0, *cs_b0, *cs_w2, *cs_b2;  // csize_embedder.mlp
+  const float *ar_w0, *ar_b0, *ar_w2, *ar_b2;  // ar_embedder.mlp
+  const float *tb_w, *tb_b;                    // t_block.1
+  const bf16 *y_fc1, *y_fc2;
+  const float *y_b1, *y_b2;
+  const float *fin_table, *fin_w, *fin_b;
+
+  // caches owned by the handle
+  float* pos = nullptr;  // (gh*gw, D) table for the last (gh, gw)
+  int pos_gh = 0, pos_gw = 0;
+  bf16* ykv = nullptr;   // [nblk][sumL][2D] caption K/V of the last caption
+  long ykv_cap = 0;      // capacity in elements
+  int ykv_sumL = -1;
+};
+
+int dit_create(const DitConfig& cfg, Dit** out);
+void dit_destroy(Dit* d);
+int dit_load_param(Dit* d, const char* name, const float* src_dev, long numel, cudaStream_t s);
+size_t dit_workspace_bytes(const Dit* d, int B, int H, int W, int sumL);
+
+struct DitForwardArgs {
+  const float* x = nullptr;         // (B, in_ch, H, W)
+  const float* c = nullptr;         // (B, in_ch, H, W) or null -> plain base path
+  const float* timestep = nullptr;  // (B)
+  const float* y = nullptr;         // (rows, caption_ch) caption embeddings (all tokens, padded)
+  const int* y_index = nullptr;     // device (sumL): rows of y that are valid, sample-major
+  const int* kv_off = nullptr;      // device (B): first packed row of each sample
+  const int* kv_len = nullptr;      // device (B): valid tokens of each sample
+  const float* img_hw = nullptr;    // device (B, 2)
+  const float* aspect = nullptr;    // device (B)
+  float* out = nullptr;             // (B, out_ch, H, W)
+  int B = 0, H = 0, W = 0, sumL = 0;
+  int reuse_caption = 0;            // 1: caption K/V of the previous call are still valid
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+};
+
+int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s);
+
+}  // namespace ir

@@ -1,0 +1,386 @@
+// Fused, vectorised elementwise / reduction kernels of the DiT + ControlNet forward (HBM-bound work).
+// Each kernel cites the reference lines it restates; see elementwise.cuh for the launcher contracts.
+#include "elementwise.cuh"
+
+namespace ir {
+
+static inline int div_up(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------ pos-embed
+// PixArt.py:258-307. pos = float32(arange / (grid/base) / pe); angles and sin/cos in float64; the first D/2
+// channels encode the w-coordinate ("w goes first"), the last D/2 the h-coordinate; each half is [sin | cos].
+__global__ void pos_embed_kernel(float* __restrict__ table, int gh, int gw, int D, float div_h, float div_w,
+                                 float pe) {
+  const int quarter = D / 4;
+  const long total = (long)gh * gw * D;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % D);
+    const int t = (int)(idx / D);
+    const int i = t / gw, j = t % gw;
+    const int half = d / (2 * quarter);        // 0: from w-coordinate, 1: from h-coordinate
+    const int r = d - half * 2 * quarter;
+    const int is_cos = r / quarter;
+    const int k = r - is_cos * quarter;
+    float pos = half == 0 ? ((float)j / div_w) : ((float)i / div_h);
+    pos = pos / pe;
+    const double omega = 1.0 / pow(10000.0, (double)k / (double)quarter);
+    const double ang = (double)pos * omega;
+    table[idx] = (float)(is_cos ? cos(ang) : sin(ang));
+  }
+}
+
+int pos_embed_launch(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, cudaStream_t s) {
+  IR_REQUIRE(D % 4 == 0 && gh > 0 && gw > 0 && base_size > 0, "pos_embed: bad arguments");
+  const float div_h = (float)((double)gh / (double)base_size);
+  const float div_w = (float)((double)gw / (double)base_size);
+  const long total = (long)gh * gw * D;
+  pos_embed_kernel<<<div_up(total, 256) > 4096 ? 4096 : div_up(total, 256), 256, 0, s>>>(table, gh, gw, D, div_h,
+                                                                                        div_w, pe_interpolation);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ patch-embed
+// PixArtMS.py:38,42-44: Conv2d(C, D, k=2, s=2) then flatten(2).transpose(1,2); + pos_embed (pixart_controlnet.py:215).
+__global__ void patch_embed_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                   const float* __restrict__ bias, const float* __restrict__ pos,
+                                   float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int B, int C, int H, int W,
+                                   int D) {
+  const int gh = H / 2, gw = W / 2;
+  const int T = gh * gw;
+  const int dv = D / 4;
+  const long total = (long)B * T * dv;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(idx % dv) * 4;
+    const long bt = idx / dv;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const int i = t / gw, j = t % gw;
+    float4 acc = *reinterpret_cast<const float4*>(bias + d4);
+    for (int c = 0; c < C; ++c) {
+      const float* xp = x + (((long)b * C + c) * H + 2 * i) * W + 2 * j;
+      const float2 r0 = *reinterpret_cast<const float2*>(xp);
+      const float2 r1 = *reinterpret_cast<const float2*>(xp + W);
+      const float xv[4] = {r0.x, r0.y, r1.x, r1.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + (long)(c * 4 + k) * D + d4);
+        acc.x += w4.x * xv[k];
+        acc.y += w4.y * xv[k];
+        acc.z += w4.z * xv[k];
+        acc.w += w4.w * xv[k];
+      }
+    }
+    const float4 p4 = *reinterpret_cast<const float4*>(pos + (long)t * D + d4);
+    acc.x += p4.x;
+    acc.y += p4.y;
+    acc.z += p4.z;
+    acc.w += p4.w;
+    const long o = bt * D + d4;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = acc;
+    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  }
+}
+
+int patch_embed_launch(const float* x, const float* wt, const float* bias, const float* pos, float* out_f32,
+                       bf16* out_bf16, int B, int C, int H, int W, int D, cudaStream_t s) {
+  IR_REQUIRE(H % 2 == 0 && W % 2 == 0 && D % 4 == 0, "patch_embed: H, W must be even and D %% 4 == 0");
+  const long total = (long)B * (H / 2) * (W / 2) * (D / 4);
+  patch_embed_kernel<<<div_up(total, 256), 256, 0, s>>>(x, wt, bias, pos, out_f32, out_bf16, B, C, H, W, D);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sinusoid
+// TimestepEmbedder.timestep_embedding, PixArt_blocks.py:336-353 (dim 256, cos first).
+__global__ void sinusoid_kernel(const float* __restrict__ vals, float* __restrict__ out, int rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 128) return;
+  const int r = idx / 128, i = idx % 128;
+  const float freq = expf(-logf(10000.0f) * (float)i / 128.0f);
+  const float arg = vals[r] * freq;
+  out[(long)r * 256 + i] = cosf(arg);
+  out[(long)r * 256 + 128 + i] = sinf(arg);
+}
+
+int sinusoid_launch(const float* vals, float* out, int rows, cudaStream_t s) {
+  sinusoid_kernel<<<div_up((long)rows * 128, 128), 128, 0, s>>>(vals, out, rows);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ small linear
+// Conditioning MLPs (TimestepEmbedder / SizeEmbedder / t_block; PixArt_blocks.py:329-333,356-358,372-393;
+// PixArtMS.py:134-137): a handful of rows against fp32 weights, bandwidth-bound on the weight read.
+template <int RC>
+__global__ void small_linear_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ y, long ldy, int rows_per_group,
+                                    long group_stride, int rows, int N, int K, int act_in, int act_out, int accumulate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* wrow = W + (long)warp * K;
+  for (int r0 = 0; r0 < rows; r0 += RC) {
+    float acc[RC];
+#pragma unroll
+    for (int r = 0; r < RC; ++r) acc[r] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        if (r0 + r < rows) {
+          float4 x4 = *reinterpret_cast<const float4*>(x + (long)(r0 + r) * ldx + k);
+          if (act_in == ACT_SILU) {
+            x4.x = silu(x4.x);
+            x4.y = silu(x4.y);
+            x4.z = silu(x4.z);
+            x4.w = silu(x4.w);
+          }
+          acc[r] += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RC; ++r) {
+      const float v = warp_sum(acc[r]);
+      if (lane == 0 && r0 + r < rows) {
+        float o = v + (bias ? bias[warp] : 0.f);
+        if (act_out == ACT_SILU) o = silu(o);
+        const int rr = r0 + r;
+        float* dst = y + (long)(rr / rows_per_group) * group_stride + (long)(rr % rows_per_group) * ldy + warp;
+        *dst = accumulate ? (*dst + o) : o;
+      }
+    }
+  }
+}
+
+int small_linear_launch(const float* x, long ldx, const float* W, const float* bias, float* y, long ldy,
+                        int rows_per_group, long group_stride, int rows, int N, int K, int act_in, int act_out,
+                        int accumulate, cudaStream_t s) {
+  IR_REQUIRE(K % 4 == 0 && ldx % 4 == 0, "small_linear: K and ldx must be multiples of 4");
+  IR_REQUIRE(rows_per_group > 0, "small_linear: rows_per_group must be positive");
+  small_linear_kernel<4><<<div_up((long)N * 32, 256), 256, 0, s>>>(x, ldx, W, bias, y, ldy, rows_per_group,
+                                                                   group_stride, rows, N, K, act_in, act_out,
+                                                                   accumulate);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ adaLN table
+__global__ void adaln_table_kernel(const float* __restrict__ tables, const float* __restrict__ t0,
+                                   float* __restrict__ mod, int nblk, int B, int sixD) {
+  const long total = (long)nblk * B * sixD / 4;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const long e = idx * 4;
+    const int d = (int)(e % sixD);
+    const long bb = e / sixD;
+    const int b = (int)(bb % B), blk = (int)(bb / B);
+    const float4 a = *reinterpret_cast<const float4*>(tables + (long)blk * sixD + d);
+    const float4 c = *reinterpret_cast<const float4*>(t0 + (long)b * sixD + d);
+    *reinterpret_cast<float4*>(mod + e) = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+}
+
+int adaln_table_launch(const float* tables, const float* t0, float* mod, int nblk, int B, int D, cudaStream_t s) {
+  const long total = (long)nblk * B * 6 * D / 4;
+  adaln_table_kernel<<<div_up(total, 256), 256, 0, s>>>(tables, t0, mod, nblk, B, 6 * D);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LN + modulate
+// One warp per token row; the row lives in registers (V float4 per lane), two-pass mean / variance in fp32.
+template <int V>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, bf16* __restrict__ out,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, long mod_stride, int rows,
+                                                          int T) {
+  constexpr int D = V * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long)row * D;
+  float4 v[V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(sum) * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean;
+    v[i].y -= mean;
+    v[i].z -= mean;
+    v[i].w -= mean;
+    sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+  const int b = row / T;
+  const float* sh = shift + (long)b * mod_stride;
+  const float* sc = scale + (long)b * mod_stride;
+  bf16* orow = out + (long)row * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 s4 = *reinterpret_cast<const float4*>(sh + c);
+    const float4 c4 = *reinterpret_cast<const float4*>(sc + c);
+    const float a0 = v[i].x * rstd * (1.0f + c4.x) + s4.x;
+    const float a1 = v[i].y * rstd * (1.0f + c4.y) + s4.y;
+    const float a2 = v[i].z * rstd * (1.0f + c4.z) + s4.z;
+    const float a3 = v[i].w * rstd * (1.0f + c4.w) + s4.w;
+    *reinterpret_cast<uint2*>(orow + c) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+  }
+}
+
+int ln_modulate_launch(const float* x, bf16* out, const float* shift, const float* scale, long mod_stride, int rows,
+                       int T, int D, cudaStream_t s) {
+  IR_REQUIRE(D == 1152, "ln_modulate: hidden size %d unsupported (kernel is specialised for 1152)", D);
+  ln_modulate_kernel<9><<<div_up(rows, 8), 256, 0, s>>>(x, out, shift, scale, mod_stride, rows, T);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ final layer
+// T2IFinalLayer (PixArt_blocks.py:271-275) + unpatchify (pixart_controlnet.py:165-177): one warp per token.
+template <int V, int NOUT>
+__global__ void __launch_bounds__(256) final_layer_kernel(const float* __restrict__ x, const float* __restrict__ table,
+                                                          const float* __restrict__ t, const float* __restrict__ W,
+                                                          const float* __restrict__ bias, float* __restrict__ out,
+                                                          int rows, int gh, int gw, int cout) {
+  constexpr int D = V * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int T = gh * gw;
+  const int b = row / T, tok = row % T;
+  const float* xr = x + (long)row * D;
+  float4 v[V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(sum) * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean;
+    v[i].y -= mean;
+    v[i].z -= mean;
+    v[i].w -= mean;
+    sq += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+  const float* tb = t + (long)b * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 t4 = *reinterpret_cast<const float4*>(tb + c);
+    const float4 s4 = *reinterpret_cast<const float4*>(table + c);      // shift row
+    const float4 c4 = *reinterpret_cast<const float4*>(table + D + c);  // scale row
+    v[i].x = v[i].x * rstd * (1.0f + c4.x + t4.x) + (s4.x + t4.x);
+    v[i].y = v[i].y * rstd * (1.0f + c4.y + t4.y) + (s4.y + t4.y);
+    v[i].z = v[i].z * rstd * (1.0f + c4.z + t4.z) + (s4.z + t4.z);
+    v[i].w = v[i].w * rstd * (1.0f + c4.w + t4.w) + (s4.w + t4.w);
+  }
+  float mine = 0.f;  // lane o keeps output feature o
+#pragma unroll 4
+  for (int o = 0; o < NOUT; ++o) {
+    const float* wr = W + (long)o * D;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wr + (i * 32 + lane) * 4);
+      acc += v[i].x * w4.x + v[i].y * w4.y + v[i].z * w4.z + v[i].w * w4.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == o) mine = acc + bias[o];
+  }
+  if (lane < NOUT) {
+    // feature o = (p*2 + q)*cout + c  ->  imgs[b][c][2i+p][2j+q]
+    const int c = lane % cout, pq = lane / cout;
+    const int pp = pq >> 1, qq = pq & 1;
+    const int i = tok / gw, j = tok % gw;
+    out[(((long)b * cout + c) * (2 * gh) + (2 * i + pp)) * (2 * gw) + (2 * j + qq)] = mine;
+  }
+}
+
+int final_layer_launch(const float* x, const float* table, const float* t, const float* W, const float* bias,
+                       float* out, int B, int gh, int gw, int D, int cout, cudaStream_t s) {
+  IR_REQUIRE(D == 1152 && cout == 8, "final_layer: specialised for hidden 1152, 8 output channels, patch 2");
+  const int rows = B * gh * gw;
+  final_layer_kernel<9, 32><<<div_up(rows, 8), 256, 0, s>>>(x, table, t, W, bias, out, rows, gh, gw, cout);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ caption gather
+__global__ void gather_rows_kernel(const float* __restrict__ y, const int* __restrict__ idx, bf16* __restrict__ out,
+                                   int rows, int K4) {
+  const long total = (long)rows * K4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / K4), c = (int)(i % K4);
+    const float4 v = *reinterpret_cast<const float4*>(y + ((long)idx[r] * K4 + c) * 4);
+    *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+int gather_rows_launch(const float* y, const int* idx, bf16* out, int rows, int K, cudaStream_t s) {
+  IR_REQUIRE(K % 4 == 0, "gather_rows: K must be a multiple of 4");
+  if (rows == 0) return IR_OK;
+  gather_rows_kernel<<<div_up((long)rows * (K / 4), 256), 256, 0, s>>>(y, idx, out, rows, K / 4);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ eps -> x0
+__global__ void eps_to_x0_kernel(const float* __restrict__ x, const float* __restrict__ mo, float* __restrict__ x0,
+                                 int B, int C, int HW, float sa, float sb) {
+  const long total = (long)B * C * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / ((long)C * HW);
+    const long rem = i - b * (long)C * HW;
+    const float eps = mo[b * 2 * C * HW + rem];
+    x0[i] = (x[i] - sb * eps) / sa;
+  }
+}
+
+int eps_to_x0_launch(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
+                     float sqrt_one_minus_abar, cudaStream_t s) {
+  const long total = (long)B * C * HW;
+  eps_to_x0_kernel<<<div_up(total, 256), 256, 0, s>>>(x, model_out, x0, B, C, HW, sqrt_abar, sqrt_one_minus_abar);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long n4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i * 4);
+    *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+int f32_to_bf16_launch(const float* x, bf16* out, long n, cudaStream_t s) {
+  IR_REQUIRE(n % 4 == 0, "f32_to_bf16: n must be a multiple of 4");
+  const long n4 = n / 4;
+  int grid = div_up(n4, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  f32_to_bf16_kernel<<<grid, 256, 0, s>>>(x, out, n4);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+}  // namespace ir

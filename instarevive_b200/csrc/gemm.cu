@@ -1,0 +1,504 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA (128B-swizzled tiles) -> shared memory ring ->
+// tcgen05.mma with fp32 accumulators in TMEM (double-buffered) -> tcgen05.ld epilogue with fused
+// bias / GELU-tanh / gate*(.)+fp32 residual. The same kernel runs the VAE decoder's 3x3 convolutions as an
+// implicit GEMM: the A tile of one (tap, channel-chunk) K-block is a 4-D TMA box over the NHWC activation
+// whose out-of-bounds elements (the zero padding) are filled by the TMA unit.
+//
+// Replaces, on the reference side, every nn.Linear of diffusion/model/nets/PixArt_blocks.py:47-55,130,156,
+// PixArtMS.py:66-67 (timm Mlp), pixart_controlnet.py:31-36 and the Conv2d 3x3 / 1x1 layers of
+// ldm/modules/diffusionmodules/model.py:57-61,103-129,160-179.
+#include "gemm.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace ir {
+
+static constexpr int BM = 128;       // rows per CTA tile == UMMA M == TMEM lanes
+static constexpr int BK = 64;        // bf16 elements per K-block == one 128 B swizzle row
+static constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
+static constexpr int CONV_BW = 16;   // conv tile: 16 x 8 output pixels
+static constexpr int CONV_BH = 8;
+static constexpr int STG_LD = 36;    // staging row stride in floats (32 + 4 pad: conflict-free v4 stores)
+static constexpr int NUM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STG_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+struct GemmDev {
+  int M, N, K;
+  int k_blocks;    // K-blocks per tile
+  int m_blocks;    // M tiles per batch entry (per image for conv)
+  int n_blocks;
+  int batch;
+  int num_tiles;
+  // conv geometry
+  int H, Wd, tiles_x, c_blocks;
+  // epilogue
+  float alpha;
+  const float* bias;
+  long stride_bias;
+  int a_shared;  // all batch entries read A at batch coordinate 0
+  bf16* out_bf16;
+  const bf16* resid_bf16;
+  long ldo_b, stride_ob;
+  float* out_f32;
+  const float* resid_f32;
+  long ldo_f, stride_of;
+  const float* gate;
+  long gate_ld;
+  int rows_per_gate;
+};
+
+template <int BN, int EPI, bool CONV>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
+  float* staging = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STG_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES] TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES] MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2] MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int mb_total = p.m_blocks * p.batch;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile / mb_total;
+        const int mb = tile - n_blk * mb_total;
+        const int b = mb / p.m_blocks;
+        const int m_blk = mb - b * p.m_blocks;
+        int ty = 0, tx = 0;
+        if (CONV) {
+          ty = m_blk / p.tiles_x;
+          tx = m_blk - ty * p.tiles_x;
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (CONV) {
+            const int tap = kb / p.c_blocks;
+            const int cb = kb - tap * p.c_blocks;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
+                        ty * CONV_BH + dy, b);
+          } else {
+            tma_load_3d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
+          }
+          tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_blk * BN, CONV ? 0 : b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) inside the swizzle row: +2 in the 16 B-granular address field
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (kb == p.k_blocks - 1) umma_commit(&tfull_bar[buf]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
+    const int q = warp - 4;  // TMEM lane quarter: lanes [32q, 32q+32)
+    float* stg = staging + q * (32 * STG_LD);
+    const int col4 = (lane & 7) * 4;
+    const int rsub = lane >> 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile / mb_total;
+      const int mb = tile - n_blk * mb_total;
+      const int b = mb / p.m_blocks;
+      const int m_blk = mb - b * p.m_blocks;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+
+      // per-lane row bookkeeping for the 8 rows this lane touches after the transpose
+      long row_off[8];   // row index into the output (rows of ldo elements), -1 if masked
+      int gate_row[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = q * 32 + i * 4 + rsub;
+        if (CONV) {
+          const int ty = m_blk / p.tiles_x, tx = m_blk - ty * p.tiles_x;
+          const int y = ty * CONV_BH + (r >> 4), x = tx * CONV_BW + (r & 15);
+          row_off[i] = (y < p.H && x < p.Wd) ? ((long)b * p.H + y) * p.Wd + x : -1;
+          gate_row[i] = 0;
+        } else {
+          const int gm = m_blk * BM + r;
+          row_off[i] = (gm < p.M) ? (long)gm : -1;
+          gate_row[i] = gm / p.rows_per_gate;
+        }
+      }
+
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+        }
+        __syncwarp();
+
+        const int col = n_blk * BN + c * 32 + col4;
+        if (col < p.N) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (row_off[i] < 0) continue;
+            float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * STG_LD + col4);
+            a.x = a.x * p.alpha + bias4.x;
+            a.y = a.y * p.alpha + bias4.y;
+            a.z = a.z * p.alpha + bias4.z;
+            a.w = a.w * p.alpha + bias4.w;
+            if (EPI == EPI_BF16_GELU) {
+              a.x = gelu_tanh(a.x);
+              a.y = gelu_tanh(a.y);
+              a.z = gelu_tanh(a.z);
+              a.w = gelu_tanh(a.w);
+            }
+            if (EPI == EPI_F32) {
+              const long o = (long)b * p.stride_of + row_off[i] * p.ldo_f + col;
+              if (p.gate) {
+                const float4 g = *reinterpret_cast<const float4*>(p.gate + (long)gate_row[i] * p.gate_ld + col);
+                a.x *= g.x;
+                a.y *= g.y;
+                a.z *= g.z;
+                a.w *= g.w;
+              }
+              if (p.resid_f32) {
+                const float4 r4 = *reinterpret_cast<const float4*>(p.resid_f32 + o);
+                a.x += r4.x;
+                a.y += r4.y;
+                a.z += r4.z;
+                a.w += r4.w;
+              }
+              *reinterpret_cast<float4*>(p.out_f32 + o) = a;
+              if (p.out_bf16) {
+                const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
+                uint2 u = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+                *reinterpret_cast<uint2*>(p.out_bf16 + ob) = u;
+              }
+            } else {
+              const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
+              if (EPI == EPI_BF16 && p.resid_bf16) {
+                const uint2 ru = *reinterpret_cast<const uint2*>(p.resid_bf16 + ob);
+                const float2 r0 = unpack_bf16x2(ru.x), r1 = unpack_bf16x2(ru.y);
+                a.x += r0.x;
+                a.y += r0.y;
+                a.z += r1.x;
+                a.w += r1.y;
+              }
+              uint2 u = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              *reinterpret_cast<uint2*>(p.out_bf16 + ob) = u;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// bf16 tensor map, innermost dimension first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
+    return IR_ERR_DRIVER;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu,%llu,%llu base %p)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                   base);
+    return IR_ERR_DRIVER;
+  }
+  return IR_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int EPI, bool CONV>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<BN, EPI, CONV>;
+  static bool configured = false;
+  if (!configured) {
+    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+    configured = true;
+  }
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, NUM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tw, p);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+template <int BN, bool CONV>
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV>(ta, tw, p, s);
+    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV>(ta, tw, p, s);
+    case EPI_F32: return launch_inst<BN, EPI_F32, CONV>(ta, tw, p, s);
+  }
+  set_last_error("gemm: unknown epilogue %d", epi);
+  return IR_ERR_INVALID;
+}
+
+static int pick_bn(long m_tiles, int N, int forced) {
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  static int env_bn = -1;
+  if (env_bn < 0) {
+    const char* e = getenv("IR_GEMM_BN");
+    env_bn = e ? atoi(e) : 0;
+  }
+  if (env_bn == 64 || env_bn == 128 || env_bn == 256) return env_bn;
+  const int sms = num_sms();
+  int best = 128;
+  double best_cost = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 64 && N <= bn / 2) continue;  // tile mostly empty
+    const long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    const double cost = (double)waves * (bn + 32);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+  IR_REQUIRE(a.A && a.W, "gemm: null operand");
+  IR_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: bad shape M=%d N=%d K=%d batch=%d", a.M, a.N, a.K,
+             a.batch);
+  IR_REQUIRE(a.N % 4 == 0, "gemm: N=%d must be a multiple of 4", a.N);
+  IR_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+             "gemm: operands must be 16-byte aligned");
+  if (a.epi == EPI_F32) {
+    IR_REQUIRE(a.out_f32 && a.ldo_f % 4 == 0, "gemm: EPI_F32 needs out_f32 with ld %% 4 == 0");
+    IR_REQUIRE(!a.out_bf16 || a.ldo_b % 4 == 0, "gemm: bf16 copy needs ld %% 4 == 0");
+  } else {
+    IR_REQUIRE(a.out_bf16 && a.ldo_b % 4 == 0, "gemm: bf16 epilogue needs out_bf16 with ld %% 4 == 0");
+  }
+  IR_REQUIRE(!a.gate || a.gate_ld % 4 == 0, "gemm: gate_ld must be a multiple of 4");
+
+  GemmDev p{};
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.batch = a.batch;
+  p.alpha = a.alpha;
+  p.bias = a.bias;
+  p.stride_bias = a.conv ? 0 : a.stride_bias;
+  p.a_shared = (!a.conv && a.batch > 1 && a.strideA == 0) ? 1 : 0;
+  p.out_bf16 = a.out_bf16;
+  p.resid_bf16 = a.resid_bf16;
+  p.ldo_b = a.ldo_b;
+  p.stride_ob = a.stride_ob;
+  p.out_f32 = a.out_f32;
+  p.resid_f32 = a.resid_f32;
+  p.ldo_f = a.ldo_f;
+  p.stride_of = a.stride_of;
+  p.gate = a.gate;
+  p.gate_ld = a.gate_ld;
+  p.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1;
+
+  CUtensorMap ta, tw;
+  long m_tiles;
+  if (a.conv) {
+    IR_REQUIRE(a.C % BK == 0, "conv: C=%d must be a multiple of %d", a.C, BK);
+    IR_REQUIRE(a.K == 9 * a.C, "conv: K=%d must equal 9*C=%d", a.K, 9 * a.C);
+    IR_REQUIRE(a.M == a.nimg * a.H * a.Wd, "conv: M mismatch");
+    IR_REQUIRE(a.batch == 1, "conv: batch must be 1 (images are folded into M)");
+    p.H = a.H;
+    p.Wd = a.Wd;
+    p.tiles_x = (a.Wd + CONV_BW - 1) / CONV_BW;
+    const int tiles_y = (a.H + CONV_BH - 1) / CONV_BH;
+    p.m_blocks = p.tiles_x * tiles_y;
+    p.batch = a.nimg;  // one "batch" entry per image
+    p.c_blocks = a.C / BK;
+    p.k_blocks = 9 * p.c_blocks;
+    // the conv epilogue indexes the output by pixel; batch strides are folded into the pixel index
+    p.stride_ob = 0;
+    p.stride_of = 0;
+    const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.Wd, (uint64_t)a.H, (uint64_t)a.nimg};
+    const uint64_t strides[3] = {(uint64_t)a.C * 2, (uint64_t)a.Wd * a.C * 2, (uint64_t)a.H * a.Wd * a.C * 2};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)CONV_BW, (uint32_t)CONV_BH, 1};
+    IR_TRY(make_map(&ta, a.A, 4, dims, strides, box));
+    m_tiles = (long)p.m_blocks * a.nimg;
+  } else {
+    IR_REQUIRE(a.lda % 8 == 0 && a.strideA % 8 == 0, "gemm: lda/strideA must be multiples of 8 elements");
+    p.m_blocks = (a.M + BM - 1) / BM;
+    p.k_blocks = (a.K + BK - 1) / BK;
+    const int ab = p.a_shared ? 1 : a.batch;
+    const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.M, (uint64_t)ab};
+    const uint64_t strides[2] = {(uint64_t)a.lda * 2, (uint64_t)(ab > 1 ? a.strideA : (long)a.M * a.lda) * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
+    IR_TRY(make_map(&ta, a.A, 3, dims, strides, box));
+    m_tiles = (long)p.m_blocks * a.batch;
+  }
+  IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
+
+  const int bn = pick_bn(m_tiles, a.N, a.force_bn);
+  p.n_blocks = (a.N + bn - 1) / bn;
+  p.num_tiles = (int)(m_tiles * p.n_blocks);
+  {
+    const int wb = a.conv ? 1 : a.batch;
+    const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)wb};
+    const uint64_t strides[2] = {(uint64_t)a.ldw * 2, (uint64_t)(wb > 1 ? a.strideW : (long)a.N * a.ldw) * 2};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)bn, 1};
+    IR_TRY(make_map(&tw, a.W, 3, dims, strides, box));
+  }
+
+  if (a.conv) {
+    switch (bn) {
+      case 64: return launch_epi<64, true>(a.epi, ta, tw, p, stream);
+      case 128: return launch_epi<128, true>(a.epi, ta, tw, p, stream);
+      default: return launch_epi<256, true>(a.epi, ta, tw, p, stream);
+    }
+  }
+  switch (bn) {
+    case 64: return launch_epi<64, false>(a.epi, ta, tw, p, stream);
+    case 128: return launch_epi<128, false>(a.epi, ta, tw, p, stream);
+    default: return launch_epi<256, false>(a.epi, ta, tw, p, stream);
+  }
+}
+
+}  // namespace ir

@@ -1,0 +1,56 @@
+// Host-side interface of the tcgen05 GEMM / implicit-GEMM convolution kernel (gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ir {
+
+enum GemmEpilogue {
+  EPI_BF16 = 0,       // out_bf16 = alpha*acc + bias (+ resid_bf16)
+  EPI_BF16_GELU = 1,  // out_bf16 = gelu_tanh(alpha*acc + bias)
+  EPI_F32 = 2,        // out_f32 = resid_f32 + gate * (alpha*acc + bias); optional bf16 copy of out_f32
+};
+
+// C[b][m][n] = sum_k A[b][m][k] * W[b][n][k]   (both operands K-major bf16, fp32 accumulation in TMEM).
+// conv != 0: A is an NHWC activation [nimg][H][Wd][C] and the kernel computes a 3x3, stride 1, pad 1
+// convolution as an implicit GEMM with K = 9*C (k = tap*C + c, tap = ky*3 + kx) and M = nimg*H*Wd;
+// W is [N][9*C].
+struct GemmArgs {
+  const bf16* A = nullptr;
+  long lda = 0;      // row stride of A in elements (plain GEMM)
+  long strideA = 0;  // batch stride of A in elements (0 with batch > 1: every batch entry reads the same A)
+  const bf16* W = nullptr;
+  long ldw = 0;
+  long strideW = 0;
+  int M = 0, N = 0, K = 0, batch = 1;
+
+  int conv = 0;
+  int nimg = 0, H = 0, Wd = 0, C = 0;
+
+  int epi = EPI_BF16;
+  float alpha = 1.0f;
+  const float* bias = nullptr;  // [N]
+  long stride_bias = 0;         // batch stride of bias in elements
+
+  bf16* out_bf16 = nullptr;
+  const bf16* resid_bf16 = nullptr;  // EPI_BF16 only; same layout as out_bf16
+  long ldo_b = 0;
+  long stride_ob = 0;
+
+  float* out_f32 = nullptr;
+  const float* resid_f32 = nullptr;  // same layout as out_f32; may alias out_f32
+  long ldo_f = 0;
+  long stride_of = 0;
+
+  const float* gate = nullptr;  // gate[(row / rows_per_gate) * gate_ld + n]
+  long gate_ld = 0;
+  int rows_per_gate = 1;
+
+  int force_bn = 0;  // 0 = heuristic; otherwise 64 / 128 / 256
+};
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+// number of kernel launches issued by this library since load (bench.py's gpu_launches counter)
+void count_launch(int n = 1);
+
+}  // namespace ir
