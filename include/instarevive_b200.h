@@ -89,6 +89,47 @@ int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* times
 int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
                  float sqrt_one_minus_abar, void* stream);
 
+/* ------------------------------------------------------------------ VAE decoder ---- */
+typedef struct ir_vae ir_vae; /* opaque: packed decoder weights */
+
+typedef struct ir_vae_config {
+  int ch;             /* 128 (configs/cldm.yaml:69-84) */
+  int z_channels;     /* 4 */
+  int out_ch;         /* 3 */
+  int num_res_blocks; /* 2 */
+  int ch_mult[4];     /* 1,2,4,4 */
+} ir_vae_config;
+
+int ir_vae_create(const ir_vae_config* cfg, ir_vae** out);
+void ir_vae_destroy(ir_vae* h);
+/* Parameter names are the reference keys: post_quant_conv.{weight,bias}, decoder.* (SURVEY 8b "VAE surface"). */
+int ir_vae_num_params(const ir_vae* h);
+int ir_vae_param_info(const ir_vae* h, int i, char* name, int name_cap, long long* numel);
+int ir_vae_load_param(ir_vae* h, const char* name, const float* src_dev, long long numel, void* stream);
+size_t ir_vae_workspace_bytes(const ir_vae* h, int B, int h_lat, int w_lat);
+/* out (B,3,8h,8w) fp32 = decode(z * in_scale) * out_scale + out_shift; z: (B,4,h,w) fp32 latents.
+ * in_scale = 1/scaling_factor and out = x/2 + 0.5 reproduce test_scripts/inference.py:116-117,140-142. */
+int ir_vae_decode(ir_vae* h, const float* z, float* out, int B, int h_lat, int w_lat, float in_scale, float out_scale,
+                  float out_shift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ tile scheduler / pixel post-processing ---- */
+/* coords: device int32 [ntiles][2] = (hi, wi) window origins from _sliding_windows (test_scripts/inference.py:40-53),
+ * multiplied by `scale` inside the kernels (1 for latents, 8 for pixels).
+ * gather: dst[t][n][c][y][x] = src[n][c][hi_t*scale + y][wi_t*scale + x]  (inference.py:130,140,144). */
+int ir_tile_gather(const float* src, float* dst, const int32_t* coords, int ntiles, int N, int C, int H, int W, int th,
+                   int tw, int scale, void* stream);
+/* blend: out = (sum of covering tiles, in tile-list order) / cover count  (inference.py:133-136,151-153). */
+int ir_tile_blend(const float* tiles, const int32_t* coords, int ntiles, float* out, int N, int C, int H, int W, int th,
+                  int tw, int scale, void* stream);
+size_t ir_wavelet_workspace_bytes(int N, int C, int H, int W);
+/* out = high_freq(content) + low_freq(style), 5-level a-trous decomposition (utils/image/align_color.py:73-119). */
+int ir_wavelet_reconstruction(const float* content, const float* style, float* out, int N, int C, int H, int W,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* adaptive_instance_normalization (utils/image/align_color.py:44-71). */
+int ir_adain(const float* content, const float* style, float* out, int N, int C, int HW, void* stream);
+/* (N,C,H,W) fp32 in [0,1] -> (N,H,W,C) uint8 with clamp and truncation (test_scripts/inference.py:159-160). */
+int ir_to_uint8(const float* img, uint8_t* out, int N, int C, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------ unit entry points (parity tests) ---- */
 /* out = epilogue(alpha * A[M,K] * W[N,K]^T + bias). epilogue: 0 bf16, 1 bf16+GELU(tanh), 2 fp32 (+gate, +resid). */
 int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int batch, long long strideA,
@@ -105,6 +146,8 @@ int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, lo
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream);
 int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream);
+/* tokens (B*T, D) fp32 = PatchEmbed(x) + pos (PixArtMS.py:22-46, pixart_controlnet.py:78-87); used by forward_c. */
+int ir_dit_patch_embed(ir_dit* h, const float* x, float* tokens, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "ir_dit_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
     "ir_dit_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ir_dit_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ir_dit_patch_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ir_eps_to_x0": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "ir_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ir_conv3x3_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -50,10 +51,11 @@ PROTOTYPES = {
     "ir_vae_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
     "ir_vae_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "ir_vae_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
-    "ir_tile_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "ir_tile_scatter_add": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "ir_tile_divide": (_i, [_vp, _vp, _ll, _vp]),
-    "ir_wavelet_reconstruction": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ir_tile_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ir_tile_blend": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ir_wavelet_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ir_wavelet_reconstruction": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ir_adain": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ir_to_uint8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

@@ -6,6 +6,8 @@
 
 #include "../../include/instarevive_b200.h"
 #include "dit.cuh"
+#include "tiles.cuh"
+#include "vae.cuh"
 
 namespace ir {
 
@@ -26,6 +28,9 @@ using namespace ir;
 
 struct ir_dit {
   Dit* d;
+};
+struct ir_vae {
+  Vae* v;
 };
 
 extern "C" {
@@ -123,9 +128,99 @@ int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* times
   return dit_forward(h->d, a, (cudaStream_t)stream);
 }
 
+int ir_dit_patch_embed(ir_dit* h, const float* x, float* tokens, int B, int H, int W, void* stream) {
+  if (!h || !x || !tokens) {
+    set_last_error("ir_dit_patch_embed: null argument");
+    return IR_ERR_INVALID;
+  }
+  return dit_patch_embed(h->d, x, tokens, B, H, W, (cudaStream_t)stream);
+}
+
 int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
                  float sqrt_one_minus_abar, void* stream) {
   return eps_to_x0_launch(x, model_out, x0, B, C, HW, sqrt_abar, sqrt_one_minus_abar, (cudaStream_t)stream);
+}
+
+int ir_vae_create(const ir_vae_config* cfg, ir_vae** out) {
+  if (!cfg || !out) {
+    set_last_error("ir_vae_create: null argument");
+    return IR_ERR_INVALID;
+  }
+  VaeConfig c;
+  c.ch = cfg->ch;
+  c.z_channels = cfg->z_channels;
+  c.out_ch = cfg->out_ch;
+  c.num_res_blocks = cfg->num_res_blocks;
+  for (int i = 0; i < 4; ++i) c.ch_mult[i] = cfg->ch_mult[i];
+  Vae* v = nullptr;
+  int st = vae_create(c, &v);
+  if (st != IR_OK) return st;
+  *out = new ir_vae{v};
+  return IR_OK;
+}
+
+void ir_vae_destroy(ir_vae* h) {
+  if (!h) return;
+  vae_destroy(h->v);
+  delete h;
+}
+
+int ir_vae_num_params(const ir_vae* h) { return h ? (int)h->v->params.size() : 0; }
+
+int ir_vae_param_info(const ir_vae* h, int i, char* name, int name_cap, long long* numel) {
+  if (!h || i < 0 || i >= (int)h->v->params.size()) {
+    set_last_error("ir_vae_param_info: index %d out of range", i);
+    return IR_ERR_INVALID;
+  }
+  const VaeParam& e = h->v->params[i];
+  if (name && name_cap > 0) {
+    strncpy(name, e.name.c_str(), (size_t)name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (numel) *numel = e.numel;
+  return IR_OK;
+}
+
+int ir_vae_load_param(ir_vae* h, const char* name, const float* src_dev, long long numel, void* stream) {
+  if (!h || !name || !src_dev) {
+    set_last_error("ir_vae_load_param: null argument");
+    return IR_ERR_INVALID;
+  }
+  return vae_load_param(h->v, name, src_dev, (long)numel, (cudaStream_t)stream);
+}
+
+size_t ir_vae_workspace_bytes(const ir_vae* h, int B, int h_lat, int w_lat) {
+  return h ? vae_workspace_bytes(h->v, B, h_lat, w_lat) : 0;
+}
+
+int ir_vae_decode(ir_vae* h, const float* z, float* out, int B, int h_lat, int w_lat, float in_scale, float out_scale,
+                  float out_shift, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) {
+    set_last_error("ir_vae_decode: null handle");
+    return IR_ERR_INVALID;
+  }
+  return vae_decode(h->v, z, out, B, h_lat, w_lat, in_scale, out_scale, out_shift, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+
+int ir_tile_gather(const float* src, float* dst, const int32_t* coords, int ntiles, int N, int C, int H, int W, int th,
+                   int tw, int scale, void* stream) {
+  return tile_gather_launch(src, dst, coords, ntiles, N, C, H, W, th, tw, scale, (cudaStream_t)stream);
+}
+int ir_tile_blend(const float* tiles, const int32_t* coords, int ntiles, float* out, int N, int C, int H, int W, int th,
+                  int tw, int scale, void* stream) {
+  return tile_blend_launch(tiles, coords, ntiles, out, N, C, H, W, th, tw, scale, (cudaStream_t)stream);
+}
+size_t ir_wavelet_workspace_bytes(int N, int C, int H, int W) { return wavelet_workspace_bytes(N, C, H, W); }
+int ir_wavelet_reconstruction(const float* content, const float* style, float* out, int N, int C, int H, int W,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return wavelet_reconstruction_launch(content, style, out, N, C, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int ir_adain(const float* content, const float* style, float* out, int N, int C, int HW, void* stream) {
+  return adain_launch(content, style, out, N, C, HW, (cudaStream_t)stream);
+}
+int ir_to_uint8(const float* img, uint8_t* out, int N, int C, int H, int W, void* stream) {
+  return to_uint8_launch(img, out, N, C, H, W, (cudaStream_t)stream);
 }
 
 int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, int K, int batch, long long strideA,

@@ -348,6 +348,26 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
   return IR_OK;
 }
 
+// position table, cached per token grid (the reference recomputes it on the host with numpy on every call)
+static int ensure_pos(Dit* d, int gh, int gw, cudaStream_t s) {
+  if (d->pos_gh == gh && d->pos_gw == gw) return IR_OK;
+  const int D = d->cfg.hidden;
+  if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
+  d->pos = nullptr;
+  d->pos_gh = d->pos_gw = 0;
+  IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)gh * gw * D * sizeof(float)));
+  IR_TRY(pos_embed_launch(d->pos, gh, gw, D, d->cfg.base_size, d->cfg.pe_interpolation, s));
+  d->pos_gh = gh;
+  d->pos_gw = gw;
+  return IR_OK;
+}
+
+int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, cudaStream_t s) {
+  IR_REQUIRE(H % 2 == 0 && W % 2 == 0 && B > 0, "dit_patch_embed: bad shape");
+  IR_TRY(ensure_pos(d, H / 2, W / 2, s));
+  return patch_embed_launch(x, d->xw_t, d->xb, d->pos, tokens, nullptr, B, d->cfg.in_ch, H, W, d->cfg.hidden, s);
+}
+
 int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   IR_REQUIRE(a.x && a.timestep && a.out && a.img_hw && a.aspect, "dit_forward: null input");
   IR_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.H % 2 == 0 && a.W % 2 == 0, "dit_forward: bad latent shape %dx%dx%d",
@@ -376,15 +396,7 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   carve(d, c.w, a.workspace, a.B, a.H, a.W, a.sumL);
   const int D = d->cfg.hidden, B = a.B;
 
-  // ---- position table (cached per token grid; reference recomputes it on the host every call)
-  if (d->pos_gh != gh || d->pos_gw != gw) {
-    if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
-    d->pos = nullptr;
-    IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)c.T * D * sizeof(float)));
-    d->pos_gh = gh;
-    d->pos_gw = gw;
-    IR_TRY(pos_embed_launch(d->pos, gh, gw, D, d->cfg.base_size, d->cfg.pe_interpolation, s));
-  }
+  IR_TRY(ensure_pos(d, gh, gw, s));
 
   // ---- conditioning: t = t_embedder(timestep) + cat(csize_embedder(img_hw), ar_embedder(ar)); t0 = t_block(t)
   {

@@ -97,5 +97,6 @@ struct DitForwardArgs {
 };
 
 int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s);
+int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, cudaStream_t s);
 
 }  // namespace ir

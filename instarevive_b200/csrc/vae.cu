@@ -1,0 +1,700 @@
+// VAE decoder (AutoencoderKL.decode, ldm/models/autoencoder.py:88-91 -> Decoder.forward,
+// ldm/modules/diffusionmodules/model.py:622-655) on NHWC bf16 activations:
+//   * 3x3 convolutions and 1x1 convolutions run on the tcgen05 implicit-GEMM / GEMM kernel (gemm.cu),
+//     bias and the residual add fused into the epilogue;
+//   * GroupNorm(32, eps 1e-6) statistics (deterministic two-stage reduction) + normalise + SiLU -> bf16,
+//     nearest x2 upsample, conv_in (K = 36) and conv_out (N = 3) are fused HBM-bound kernels here;
+//   * the mid-block single-head attention (d = 512) materialises the score matrix through the GEMM kernel
+//     (B200 has the HBM for it) with a row softmax in fp32.
+#include "vae.cuh"
+
+#include <cmath>
+
+namespace ir {
+
+static inline int div_up_l(long a, long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------ conv_in
+// post_quant_conv (1x1, zc->zc) folded into conv_in (3x3, zc->Cout, pad 1): the zero padding applies to the
+// post_quant output, so out-of-image taps contribute nothing. z: (B, zc, H, W) fp32, scaled by in_scale first
+// (the caller's `latents / scaling_factor`, test_scripts/inference.py:116,141). out: NHWC bf16.
+template <int ZC>
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ z, const float* __restrict__ pq_w,
+                                                      const float* __restrict__ pq_b, const float* __restrict__ w_t,
+                                                      const float* __restrict__ bias, bf16* __restrict__ out, int B,
+                                                      int H, int W, int Cout, float in_scale) {
+  const int tpp = Cout / 8;  // threads per pixel
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long pix = idx / tpp;
+  if (pix >= (long)B * H * W) return;
+  const int co = (int)(idx % tpp) * 8;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+  float acc[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + co);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + co + 4);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    float zin[ZC], zq[ZC];
+#pragma unroll
+    for (int c = 0; c < ZC; ++c) zin[c] = z[(((long)b * ZC + c) * H + yy) * W + xx] * in_scale;
+#pragma unroll
+    for (int o = 0; o < ZC; ++o) {
+      float v = pq_b[o];
+#pragma unroll
+      for (int c = 0; c < ZC; ++c) v += pq_w[o * ZC + c] * zin[c];
+      zq[o] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < ZC; ++c) {
+      const float* wr = w_t + (long)(tap * ZC + c) * Cout + co;
+      const float4 w0 = *reinterpret_cast<const float4*>(wr);
+      const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+      acc[0] += w0.x * zq[c]; acc[1] += w0.y * zq[c]; acc[2] += w0.z * zq[c]; acc[3] += w0.w * zq[c];
+      acc[4] += w1.x * zq[c]; acc[5] += w1.y * zq[c]; acc[6] += w1.z * zq[c]; acc[7] += w1.w * zq[c];
+    }
+  }
+  uint4 u = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                       pack_bf16x2(acc[6], acc[7]));
+  *reinterpret_cast<uint4*>(out + pix * Cout + co) = u;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// Stage 1: per (image, pixel chunk, group) partial sum / sum of squares, fixed reduction order (deterministic).
+__global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int P,
+                                                         int C, int chunk_px, int nchunks) {
+  __shared__ float sm[256][4];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int tpp = C / 8;            // threads per pixel
+  const int pps = 256 / tpp;        // pixels per block step
+  const int cs = threadIdx.x % tpp, ps = threadIdx.x / tpp;
+  const int p0 = chunk * chunk_px;
+  const int p1 = min(P, p0 + chunk_px);
+  float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
+  for (int p = p0 + ps; p < p1; p += pps) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + ((long)n * P + p) * C + cs * 8);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    s_lo += (a.x + a.y) + (b.x + b.y);
+    q_lo += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+    s_hi += (c.x + c.y) + (d.x + d.y);
+    q_hi += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+  }
+  sm[threadIdx.x][0] = s_lo;
+  sm[threadIdx.x][1] = q_lo;
+  sm[threadIdx.x][2] = s_hi;
+  sm[threadIdx.x][3] = q_hi;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;  // which: 0 = sum, 1 = sum of squares
+    const int cpg = C / 32;                                   // channels per group: 4, 8 or 16
+    float acc = 0.f;
+    for (int pp = 0; pp < pps; ++pp) {
+      if (cpg == 4) {
+        const int t = pp * tpp + (g >> 1);
+        acc += sm[t][(g & 1) * 2 + which];
+      } else {
+        const int slots = cpg / 8;
+        for (int k = 0; k < slots; ++k) {
+          const int t = pp * tpp + g * slots + k;
+          acc += sm[t][which] + sm[t][2 + which];
+        }
+      }
+    }
+    partial[(((long)n * nchunks + chunk) * 32 + g) * 2 + which] = acc;
+  }
+}
+
+// Stage 2: (mean, rstd) per (image, group); chunk partials are summed in index order in double precision.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,
+                                   double inv_count, float eps) {
+  const int n = blockIdx.x, g = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* pp = partial + (((long)n * nchunks + c) * 32 + g) * 2;
+    s += (double)pp[0];
+    q += (double)pp[1];
+  }
+  const double mean = s * inv_count;
+  double var = q * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[((long)n * 32 + g) * 2] = (float)mean;
+  stats[((long)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// Stage 3: y = act((x - mean) * rstd * gamma + beta) -> bf16; act = SiLU (x * sigmoid(x), model.py:43-45) or none.
+template <bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, long total_vec, int P, int C) {
+  const int tpp = C / 8;
+  const int cpg = C / 32;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total_vec; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % tpp) * 8;
+    const long pix = i / tpp;
+    const int n = (int)(pix / P);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
+    float v[8];
+    {
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    }
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + c0 / cpg) * 2);
+    const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + (c0 + 4) / cpg) * 2);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 st = k < 4 ? st_lo : st_hi;
+      float t = (v[k] - st.x) * st.y * gm[k] + bt[k];
+      if (SILU) t = t / (1.0f + __expf(-t));
+      v[k] = t;
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ upsample
+// F.interpolate(scale_factor=2.0, mode="nearest") on NHWC bf16 (Upsample.forward, model.py:63-67).
+__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long total_vec,
+                                                         int H, int W, int C) {
+  const int tpp = C / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total_vec; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % tpp);
+    long pix = i / tpp;
+    const int xo = (int)(pix % (2 * W));
+    pix /= 2 * W;
+    const int yo = (int)(pix % (2 * H));
+    const long n = pix / (2 * H);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((n * H + (yo >> 1)) * W + (xo >> 1)) * (long)C) + cv * 8);
+    *reinterpret_cast<uint4*>(y + i * 8) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention helpers
+// out[c][p] = in[p][col0 + c] (V^T for the P*V GEMM whose B operand must be K-major).
+__global__ void transpose_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int P, int C, long ld_in,
+                                      int col0) {
+  __shared__ bf16 tile[32][34];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* src = in + (long)blockIdx.z * P * ld_in;
+  bf16* dst = out + (long)blockIdx.z * P * C;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < P && c < C) ? src[(long)p * ld_in + col0 + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < C && p < P) dst[(long)c * P + p] = tile[threadIdx.x][r];
+  }
+}
+
+// row softmax: fp32 scores (already scaled) -> bf16 probabilities (AttnBlock.forward, model.py:195-197)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int n) {
+  __shared__ float red[8];
+  const float* row = s + (long)blockIdx.x * n;
+  bf16* orow = p + (long)blockIdx.x * n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x * 4; i < n; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + i);
+    *reinterpret_cast<uint2*>(orow + i) = make_uint2(pack_bf16x2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv),
+                                                     pack_bf16x2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv_out
+// conv_out (3x3, C -> 3, pad 1) on the normalised + SiLU'd NHWC bf16 activation; writes NCHW fp32 with a fused affine
+// out = conv * out_scale + out_shift (the caller's `/2 + 0.5`, test_scripts/inference.py:117,142). HBM-bound (N = 3).
+template <int C>
+__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
+                                                       int W, float out_scale, float out_shift) {
+  constexpr int TW = 32, TH = 8, HW_ = TW + 2, HH_ = TH + 2;
+  constexpr int LDP = C + 8;  // pixel stride in elements: (C*2 + 16) B keeps 16 B loads conflict-free
+  extern __shared__ __align__(16) uint8_t smem_co[];
+  bf16* tile = reinterpret_cast<bf16*>(smem_co);                    // [HH_*HW_][LDP]
+  float* ws = reinterpret_cast<float*>(tile + HH_ * HW_ * LDP);     // [3][9][C]
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  for (int i = threadIdx.x; i < 3 * 9 * C; i += 256) ws[i] = w[i];
+  constexpr int VPP = C / 8;
+  for (int i = threadIdx.x; i < HH_ * HW_ * VPP; i += 256) {
+    const int v = i % VPP, pp = i / VPP;
+    const int yy = y0 + pp / HW_ - 1, xx = x0 + pp % HW_ - 1;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      u = *reinterpret_cast<const uint4*>(x + (((long)n * H + yy) * W + xx) * C + v * 8);
+    *reinterpret_cast<uint4*>(tile + pp * LDP + v * 8) = u;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int ox = x0 + tx, oy = y0 + ty;
+  float acc[3] = {bias[0], bias[1], bias[2]};
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const bf16* px = tile + ((ty + tap / 3) * HW_ + tx + tap % 3) * LDP;
+    const float* w0 = ws + (0 * 9 + tap) * C;
+    const float* w1 = ws + (1 * 9 + tap) * C;
+    const float* w2 = ws + (2 * 9 + tap) * C;
+#pragma unroll 4
+    for (int v = 0; v < VPP; ++v) {
+      const uint4 u = *reinterpret_cast<const uint4*>(px + v * 8);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      const float4* wv[3] = {reinterpret_cast<const float4*>(w0 + v * 8), reinterpret_cast<const float4*>(w1 + v * 8),
+                             reinterpret_cast<const float4*>(w2 + v * 8)};
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float4 wa = wv[o][0], wb = wv[o][1];
+        acc[o] += wa.x * a.x + wa.y * a.y + wa.z * b.x + wa.w * b.y + wb.x * c.x + wb.y * c.y + wb.z * d.x + wb.w * d.y;
+      }
+    }
+  }
+  if (ox < W && oy < H) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) out[(((long)n * 3 + o) * H + oy) * W + ox] = acc[o] * out_scale + out_shift;
+  }
+}
+
+// ================================================================================================ handle
+static long align64(long v) { return (v + 63) / 64 * 64; }
+
+static void vae_add(Vae* v, const std::string& name, int kind, long numel, int cout, int cin, int k) {
+  VaeParam p;
+  p.name = name;
+  p.kind = kind;
+  p.numel = numel;
+  p.cout = cout;
+  p.cin = cin;
+  p.k = k;
+  if (kind == VP_CONV_BF16) {
+    p.offset = v->wb_elems;
+    v->wb_elems = align64(v->wb_elems + numel);
+  } else {
+    p.offset = v->wf_elems;
+    v->wf_elems = align64(v->wf_elems + numel);
+  }
+  v->index[name] = (int)v->params.size();
+  v->params.push_back(p);
+}
+
+static void vae_add_conv(Vae* v, const std::string& name, int cout, int cin, int k, int kind = VP_CONV_BF16) {
+  vae_add(v, name + ".weight", kind, (long)cout * cin * k * k, cout, cin, k);
+  vae_add(v, name + ".bias", VP_F32, cout, cout, 1, 1);
+}
+static void vae_add_norm(Vae* v, const std::string& name, int c) {
+  vae_add(v, name + ".weight", VP_F32, c, c, 1, 1);
+  vae_add(v, name + ".bias", VP_F32, c, c, 1, 1);
+}
+static void vae_add_res(Vae* v, const std::string& name, int cin, int cout) {
+  vae_add_norm(v, name + ".norm1", cin);
+  vae_add_conv(v, name + ".conv1", cout, cin, 3);
+  vae_add_norm(v, name + ".norm2", cout);
+  vae_add_conv(v, name + ".conv2", cout, cout, 3);
+  if (cin != cout) vae_add_conv(v, name + ".nin_shortcut", cout, cin, 1);
+}
+
+int vae_create(const VaeConfig& cfg, Vae** out) {
+  IR_REQUIRE(cfg.z_channels == 4 && cfg.out_ch == 3, "vae: z_channels 4 and 3 output channels expected");
+  IR_REQUIRE(cfg.ch % 64 == 0, "vae: ch must be a multiple of 64");
+  Vae* v = new Vae();
+  v->cfg = cfg;
+  const std::string d = "decoder";
+  int block_in = cfg.ch * cfg.ch_mult[3];
+  vae_add_conv(v, "post_quant_conv", cfg.z_channels, cfg.z_channels, 1, VP_F32);
+  vae_add_conv(v, d + ".conv_in", block_in, cfg.z_channels, 3, VP_CONVIN_F32);
+  vae_add_res(v, d + ".mid.block_1", block_in, block_in);
+  vae_add_norm(v, d + ".mid.attn_1.norm", block_in);
+  // q, k, v weights are registered back to back so that one GEMM with N = 3C produces all three
+  vae_add(v, d + ".mid.attn_1.q.weight", VP_CONV_BF16, (long)block_in * block_in, block_in, block_in, 1);
+  vae_add(v, d + ".mid.attn_1.k.weight", VP_CONV_BF16, (long)block_in * block_in, block_in, block_in, 1);
+  vae_add(v, d + ".mid.attn_1.v.weight", VP_CONV_BF16, (long)block_in * block_in, block_in, block_in, 1);
+  vae_add(v, d + ".mid.attn_1.q.bias", VP_F32, block_in, block_in, 1, 1);
+  vae_add(v, d + ".mid.attn_1.k.bias", VP_F32, block_in, block_in, 1, 1);
+  vae_add(v, d + ".mid.attn_1.v.bias", VP_F32, block_in, block_in, 1, 1);
+  vae_add_conv(v, d + ".mid.attn_1.proj_out", block_in, block_in, 1);
+  vae_add_res(v, d + ".mid.block_2", block_in, block_in);
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    const int block_out = cfg.ch * cfg.ch_mult[lvl];
+    for (int b = 0; b < cfg.num_res_blocks + 1; ++b) {
+      vae_add_res(v, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), block_in, block_out);
+      block_in = block_out;
+    }
+    if (lvl != 0) vae_add_conv(v, d + ".up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+  }
+  vae_add_norm(v, d + ".norm_out", block_in);
+  vae_add_conv(v, d + ".conv_out", cfg.out_ch, block_in, 3, VP_CONVOUT_F32);
+  if (cudaMalloc(&v->wb, (size_t)v->wb_elems * sizeof(bf16)) != cudaSuccess ||
+      cudaMalloc(&v->wf, (size_t)v->wf_elems * sizeof(float)) != cudaSuccess) {
+    set_last_error("vae_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    vae_destroy(v);
+    return IR_ERR_CUDA;
+  }
+  *out = v;
+  return IR_OK;
+}
+
+void vae_destroy(Vae* v) {
+  if (!v) return;
+  cudaFree(v->wb);
+  cudaFree(v->wf);
+  delete v;
+}
+
+// (Cout, Cin, k, k) fp32 -> (Cout, k*k*Cin) bf16, tap-major K (k = (ky*3 + kx)*Cin + c): the layout of the implicit GEMM
+__global__ void pack_conv_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int cout, int cin, int kk) {
+  const long total = (long)cout * cin * kk;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int tap = (int)((i / cin) % kk);
+    const int o = (int)(i / ((long)cin * kk));
+    dst[i] = __float2bfloat16(src[((long)o * cin + c) * kk + tap]);
+  }
+}
+// (Cout, Cin, 3, 3) fp32 -> [tap*Cin + c][Cout] fp32 (conv_in: coalesced over Cout)
+__global__ void pack_convin_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin) {
+  const long total = (long)cout * cin * 9;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % cout);
+    const int c = (int)((i / cout) % cin);
+    const int tap = (int)(i / ((long)cout * cin));
+    dst[i] = src[((long)o * cin + c) * 9 + tap];
+  }
+}
+// (3, Cin, 3, 3) fp32 -> [o][tap][c] fp32 (conv_out)
+__global__ void pack_convout_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin) {
+  const long total = (long)cout * cin * 9;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int tap = (int)((i / cin) % 9);
+    const int o = (int)(i / ((long)cin * 9));
+    dst[i] = src[((long)o * cin + c) * 9 + tap];
+  }
+}
+
+int vae_load_param(Vae* v, const char* name, const float* src, long numel, cudaStream_t s) {
+  auto it = v->index.find(name);
+  if (it == v->index.end()) {
+    set_last_error("vae_load_param: unknown parameter '%s'", name);
+    return IR_ERR_INVALID;
+  }
+  VaeParam& p = v->params[it->second];
+  IR_REQUIRE(numel == p.numel, "vae_load_param: '%s' has %ld elements, expected %ld", name, numel, p.numel);
+  const int grid = div_up_l(numel, 256);
+  switch (p.kind) {
+    case VP_CONV_BF16:
+      pack_conv_bf16_kernel<<<grid, 256, 0, s>>>(src, v->wb + p.offset, p.cout, p.cin, p.k * p.k);
+      break;
+    case VP_CONVIN_F32:
+      pack_convin_kernel<<<grid, 256, 0, s>>>(src, v->wf + p.offset, p.cout, p.cin);
+      break;
+    case VP_CONVOUT_F32:
+      pack_convout_kernel<<<grid, 256, 0, s>>>(src, v->wf + p.offset, p.cout, p.cin);
+      break;
+    default:
+      IR_CUDA_CHECK(cudaMemcpyAsync(v->wf + p.offset, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  IR_CUDA_CHECK(cudaGetLastError());
+  p.loaded = true;
+  return IR_OK;
+}
+
+// ================================================================================================ decode
+struct VaeWs {
+  bf16* buf[4];
+  bf16 *qkv, *vt, *pm;
+  float *scores, *partial, *stats;
+};
+
+static const int GN_MAX_CHUNKS = 2048;
+
+static size_t vae_carve(const Vae* v, VaeWs& w, void* base, int B, int h, int wd) {
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    off = (off + 255) & ~size_t(255);
+    void* p = b ? b + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  // largest activation over the decoder schedule (pixels x channels)
+  long cmax = 0;
+  {
+    long Hc = h, Wc = wd, C = (long)v->cfg.ch * v->cfg.ch_mult[3];
+    cmax = (long)B * Hc * Wc * C;
+    for (int lvl = 3; lvl >= 0; --lvl) {
+      const long Cout = (long)v->cfg.ch * v->cfg.ch_mult[lvl];
+      cmax = std::max(cmax, (long)B * Hc * Wc * std::max(C, Cout));
+      C = Cout;
+      if (lvl != 0) {
+        Hc *= 2;
+        Wc *= 2;
+        cmax = std::max(cmax, (long)B * Hc * Wc * C);
+      }
+    }
+  }
+  for (int i = 0; i < 4; ++i) w.buf[i] = reinterpret_cast<bf16*>(take((size_t)cmax * sizeof(bf16)));
+  const long P = (long)h * wd, C = (long)v->cfg.ch * v->cfg.ch_mult[3];
+  w.qkv = reinterpret_cast<bf16*>(take((size_t)B * P * 3 * C * sizeof(bf16)));
+  w.vt = reinterpret_cast<bf16*>(take((size_t)P * C * sizeof(bf16)));
+  w.pm = reinterpret_cast<bf16*>(take((size_t)P * P * sizeof(bf16)));
+  w.scores = reinterpret_cast<float*>(take((size_t)P * P * sizeof(float)));
+  w.partial = reinterpret_cast<float*>(take((size_t)B * GN_MAX_CHUNKS * 32 * 2 * sizeof(float)));
+  w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
+  return (off + 255) & ~size_t(255);
+}
+
+size_t vae_workspace_bytes(const Vae* v, int B, int h, int w) {
+  VaeWs ws;
+  return vae_carve(v, ws, nullptr, B, h, w);
+}
+
+struct VCtx {
+  Vae* v;
+  VaeWs w;
+  int B;
+  cudaStream_t s;
+};
+
+template <typename T>
+static const T* vp(const Vae* v, const std::string& name) {
+  auto it = v->index.find(name);
+  if (it == v->index.end()) return nullptr;
+  const VaeParam& p = v->params[it->second];
+  if (p.kind == VP_CONV_BF16) return reinterpret_cast<const T*>(v->wb + p.offset);
+  return reinterpret_cast<const T*>(v->wf + p.offset);
+}
+
+// y = act(GroupNorm(x)); x, y: (B, P, C) NHWC bf16
+static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, int P, int C, bool silu_act) {
+  IR_REQUIRE(C % 32 == 0 && (C / 32 == 4 || C / 32 == 8 || C / 32 == 16), "group_norm: C=%d unsupported", C);
+  int chunk_px = 256;
+  while (div_up_l(P, chunk_px) * (long)c.B > 1184 && chunk_px < (1 << 20)) chunk_px *= 2;
+  const int nchunks = div_up_l(P, chunk_px);
+  IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
+  gn_partial_kernel<<<dim3(nchunks, c.B), 256, 0, c.s>>>(x, c.w.partial, P, C, chunk_px, nchunks);
+  IR_CUDA_CHECK(cudaGetLastError());
+  gn_finalize_kernel<<<c.B, 32, 0, c.s>>>(c.w.partial, c.w.stats, nchunks, 1.0 / ((double)P * (C / 32)), 1e-6f);
+  IR_CUDA_CHECK(cudaGetLastError());
+  const long total_vec = (long)c.B * P * C / 8;
+  int grid = div_up_l(total_vec, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  const float* gamma = vp<float>(c.v, name + ".weight");
+  const float* beta = vp<float>(c.v, name + ".bias");
+  if (silu_act)
+    gn_apply_kernel<true><<<grid, 256, 0, c.s>>>(x, y, c.w.stats, gamma, beta, total_vec, P, C);
+  else
+    gn_apply_kernel<false><<<grid, 256, 0, c.s>>>(x, y, c.w.stats, gamma, beta, total_vec, P, C);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch(3);
+  return IR_OK;
+}
+
+static int conv3x3(VCtx& c, const std::string& name, const bf16* x, bf16* y, const bf16* resid, int H, int W, int Cin,
+                   int Cout) {
+  GemmArgs g;
+  g.A = x;
+  g.W = vp<bf16>(c.v, name + ".weight");
+  g.ldw = 9L * Cin;
+  g.M = c.B * H * W;
+  g.N = Cout;
+  g.K = 9 * Cin;
+  g.conv = 1;
+  g.nimg = c.B;
+  g.H = H;
+  g.Wd = W;
+  g.C = Cin;
+  g.epi = EPI_BF16;
+  g.bias = vp<float>(c.v, name + ".bias");
+  g.out_bf16 = y;
+  g.resid_bf16 = resid;
+  g.ldo_b = Cout;
+  return gemm_launch(g, c.s);
+}
+
+static int conv1x1(VCtx& c, const bf16* wgt, const float* bias, const bf16* x, bf16* y, const bf16* resid, long M,
+                   int Cin, int Cout) {
+  GemmArgs g;
+  g.A = x;
+  g.lda = Cin;
+  g.W = wgt;
+  g.ldw = Cin;
+  g.M = (int)M;
+  g.N = Cout;
+  g.K = Cin;
+  g.epi = EPI_BF16;
+  g.bias = bias;
+  g.out_bf16 = y;
+  g.resid_bf16 = resid;
+  g.ldo_b = Cout;
+  return gemm_launch(g, c.s);
+}
+
+// ResnetBlock.forward (model.py:131-151); h lives in buf[cur]; returns the index of the buffer holding the result
+static int res_block(VCtx& c, const std::string& name, int& cur, int H, int W, int Cin, int Cout) {
+  const int P = H * W;
+  bf16* x = c.w.buf[cur];
+  bf16* t1 = c.w.buf[(cur + 1) & 3];
+  bf16* t2 = c.w.buf[(cur + 2) & 3];
+  bf16* t3 = c.w.buf[(cur + 3) & 3];
+  IR_TRY(group_norm(c, name + ".norm1", x, t1, P, Cin, true));
+  IR_TRY(conv3x3(c, name + ".conv1", t1, t2, nullptr, H, W, Cin, Cout));
+  IR_TRY(group_norm(c, name + ".norm2", t2, t1, P, Cout, true));
+  const bf16* skip = x;
+  if (Cin != Cout) {
+    IR_TRY(conv1x1(c, vp<bf16>(c.v, name + ".nin_shortcut.weight"), vp<float>(c.v, name + ".nin_shortcut.bias"), x, t2,
+                   nullptr, (long)c.B * P, Cin, Cout));
+    skip = t2;
+  }
+  IR_TRY(conv3x3(c, name + ".conv2", t1, t3, skip, H, W, Cout, Cout));
+  cur = (cur + 3) & 3;
+  return IR_OK;
+}
+
+// AttnBlock.forward (model.py:181-205)
+static int attn_block(VCtx& c, const std::string& name, int& cur, int H, int W, int C) {
+  const int P = H * W;
+  bf16* x = c.w.buf[cur];
+  bf16* hn = c.w.buf[(cur + 1) & 3];
+  bf16* ao = c.w.buf[(cur + 2) & 3];
+  bf16* y = c.w.buf[(cur + 3) & 3];
+  IR_TRY(group_norm(c, name + ".norm", x, hn, P, C, false));
+  {  // q, k, v in one GEMM: (B*P, C) x (3C, C)^T
+    GemmArgs g;
+    g.A = hn; g.lda = C; g.W = vp<bf16>(c.v, name + ".q.weight"); g.ldw = C;
+    g.M = c.B * P; g.N = 3 * C; g.K = C; g.epi = EPI_BF16; g.bias = vp<float>(c.v, name + ".q.bias");
+    g.out_bf16 = c.w.qkv; g.ldo_b = 3 * C;
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  const float scale = 1.0f / sqrtf((float)C);
+  for (int b = 0; b < c.B; ++b) {  // one image at a time bounds the P x P score workspace
+    const bf16* qkv = c.w.qkv + (long)b * P * 3 * C;
+    transpose_bf16_kernel<<<dim3(div_up_l(P, 32), div_up_l(C, 32), 1), dim3(32, 8), 0, c.s>>>(qkv, c.w.vt, P, C, 3L * C,
+                                                                                                2 * C);
+    IR_CUDA_CHECK(cudaGetLastError());
+    {  // scores = q k^T * C^-1/2 (fp32)
+      GemmArgs g;
+      g.A = qkv; g.lda = 3L * C; g.W = qkv + C; g.ldw = 3L * C;
+      g.M = P; g.N = P; g.K = C; g.epi = EPI_F32; g.alpha = scale; g.out_f32 = c.w.scores; g.ldo_f = P;
+      IR_TRY(gemm_launch(g, c.s));
+    }
+    softmax_rows_kernel<<<P, 256, 0, c.s>>>(c.w.scores, c.w.pm, P);
+    IR_CUDA_CHECK(cudaGetLastError());
+    {  // h = softmax * v
+      GemmArgs g;
+      g.A = c.w.pm; g.lda = P; g.W = c.w.vt; g.ldw = P;
+      g.M = P; g.N = C; g.K = P; g.epi = EPI_BF16; g.out_bf16 = ao + (long)b * P * C; g.ldo_b = C;
+      IR_TRY(gemm_launch(g, c.s));
+    }
+    count_launch(2);
+  }
+  IR_TRY(conv1x1(c, vp<bf16>(c.v, name + ".proj_out.weight"), vp<float>(c.v, name + ".proj_out.bias"), ao, y, x,
+                 (long)c.B * P, C, C));
+  cur = (cur + 3) & 3;
+  return IR_OK;
+}
+
+int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
+               float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  IR_REQUIRE(z && out && B > 0 && h > 0 && w > 0, "vae_decode: bad arguments");
+  IR_REQUIRE(h % 2 == 0 && w % 2 == 0, "vae_decode: latent size must be even");
+  for (const VaeParam& p : v->params) IR_REQUIRE(p.loaded, "vae_decode: parameter '%s' was never loaded", p.name.c_str());
+  const size_t need = vae_workspace_bytes(v, B, h, w);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("vae_decode: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  VCtx c;
+  c.v = v;
+  c.B = B;
+  c.s = s;
+  vae_carve(v, c.w, workspace, B, h, w);
+  const std::string d = "decoder";
+  const VaeConfig& cfg = v->cfg;
+  int C = cfg.ch * cfg.ch_mult[3];
+  int H = h, W = w;
+  int cur = 0;
+  {
+    const long threads = (long)B * H * W * (C / 8);
+    conv_in_kernel<4><<<div_up_l(threads, 256), 256, 0, s>>>(z, vp<float>(v, "post_quant_conv.weight"),
+                                                             vp<float>(v, "post_quant_conv.bias"),
+                                                             vp<float>(v, d + ".conv_in.weight"),
+                                                             vp<float>(v, d + ".conv_in.bias"), c.w.buf[cur], B, H, W, C,
+                                                             in_scale);
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  IR_TRY(res_block(c, d + ".mid.block_1", cur, H, W, C, C));
+  IR_TRY(attn_block(c, d + ".mid.attn_1", cur, H, W, C));
+  IR_TRY(res_block(c, d + ".mid.block_2", cur, H, W, C, C));
+  for (int lvl = 3; lvl >= 0; --lvl) {
+    const int Cout = cfg.ch * cfg.ch_mult[lvl];
+    for (int b = 0; b < cfg.num_res_blocks + 1; ++b) {
+      IR_TRY(res_block(c, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), cur, H, W, C, Cout));
+      C = Cout;
+    }
+    if (lvl != 0) {
+      bf16* up = c.w.buf[(cur + 1) & 3];
+      const long total_vec = (long)B * (2 * H) * (2 * W) * C / 8;
+      int grid = div_up_l(total_vec, 256);
+      if (grid > 148 * 16) grid = 148 * 16;
+      upsample2x_kernel<<<grid, 256, 0, s>>>(c.w.buf[cur], up, total_vec, H, W, C);
+      IR_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      H *= 2;
+      W *= 2;
+      IR_TRY(conv3x3(c, d + ".up." + std::to_string(lvl) + ".upsample.conv", up, c.w.buf[(cur + 2) & 3], nullptr, H, W,
+                     C, C));
+      cur = (cur + 2) & 3;
+    }
+  }
+  bf16* hn = c.w.buf[(cur + 1) & 3];
+  IR_TRY(group_norm(c, d + ".norm_out", c.w.buf[cur], hn, H * W, C, true));
+  IR_REQUIRE(C == 128, "vae_decode: conv_out kernel is specialised for 128 input channels (got %d)", C);
+  {
+    constexpr int smem = (10 * 34) * (128 + 8) * 2 + 3 * 9 * 128 * 4;
+    static bool configured = false;
+    if (!configured) {
+      IR_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    conv_out_kernel<128><<<dim3(div_up_l(W, 32), div_up_l(H, 8), B), 256, smem, s>>>(
+        hn, vp<float>(v, d + ".conv_out.weight"), vp<float>(v, d + ".conv_out.bias"), out, H, W, out_scale, out_shift);
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  return IR_OK;
+}
+
+}  // namespace ir

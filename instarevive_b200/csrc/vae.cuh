@@ -1,0 +1,48 @@
+// VAE decoder handle and launcher (vae.cu).
+#pragma once
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gemm.cuh"
+
+namespace ir {
+
+struct VaeConfig {
+  int ch = 128;                   // configs/cldm.yaml:69-84
+  int z_channels = 4;
+  int out_ch = 3;
+  int num_res_blocks = 2;
+  int ch_mult[4] = {1, 2, 4, 4};
+};
+
+enum VaeParamKind { VP_F32 = 0, VP_CONV_BF16 = 1, VP_CONVIN_F32 = 2, VP_CONVOUT_F32 = 3 };
+
+struct VaeParam {
+  std::string name;  // reference state_dict key ("post_quant_conv.*", "decoder.*")
+  int kind;
+  long numel;
+  int cout, cin, k;
+  long offset;
+  bool loaded = false;
+};
+
+struct Vae {
+  VaeConfig cfg;
+  std::vector<VaeParam> params;
+  std::unordered_map<std::string, int> index;
+  bf16* wb = nullptr;
+  float* wf = nullptr;
+  long wb_elems = 0, wf_elems = 0;
+};
+
+int vae_create(const VaeConfig& cfg, Vae** out);
+void vae_destroy(Vae* v);
+int vae_load_param(Vae* v, const char* name, const float* src_dev, long numel, cudaStream_t s);
+size_t vae_workspace_bytes(const Vae* v, int B, int h, int w);
+// z: (B,4,h,w) fp32 -> out: (B,3,8h,8w) fp32 = decode(z * in_scale) * out_scale + out_shift
+int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
+               float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+}  // namespace ir

@@ -1,0 +1,55 @@
+"""One-step generator math with the reference's function names (scripts/DMD/transformer_train/generate.py:22-87),
+adapted to operator surface (A): `model` is a ControlPixArtMSHalf whose control input is the degraded latent itself
+(the authors' own usage, test_scripts/test_controlnet.py:137-139)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class DDPMSchedulerLite:
+    """The only piece of diffusers' DDPMScheduler the path reads: `alphas_cumprod` (fp32 cumprod of a linear beta
+    schedule 1e-4..2e-2 over 1000 steps; in-tree twin: get_named_beta_schedule("linear"), gaussian_diffusion.py:99-116)."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=1e-4, beta_end=2e-2):
+        betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+
+
+def eps_to_mu(scheduler, model_output, sample, timesteps):
+    """generate.py:44-51 on the (B,8,H,W) model output: keeps channels [0,4) (generate.py:84-85) and solves for x0."""
+    t = int(timesteps.reshape(-1)[0]) if torch.is_tensor(timesteps) else int(timesteps)  # tensor on GPU: one sync
+    a = float(scheduler.alphas_cumprod.to(dtype=sample.dtype)[t])
+    B, Cc = sample.shape[:2]
+    hw = sample.shape[2] * sample.shape[3]
+    s = sample.to(torch.float32).contiguous()
+    mo = model_output.to(torch.float32).contiguous()
+    if mo.shape[1] != 2 * Cc:
+        raise ValueError("model output must carry the learned-sigma half (2*C channels)")
+    out = torch.empty_like(s)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().ir_eps_to_x0(s.data_ptr(), mo.data_ptr(), out.data_ptr(), B, Cc, hw, a ** 0.5,
+                                          (1.0 - a) ** 0.5, _lib.stream_ptr()), "ir_eps_to_x0")
+    return out
+
+
+def forward_model(model, latents, timestep, prompt_embeds, prompt_attention_masks=None, c=None):
+    """generate.py:54-87: micro-conditioning from the latent size, timestep expanded to the batch."""
+    B, _, h, w = latents.shape
+    data_info = {
+        "img_hw": torch.tensor([[float(h * 8), float(w * 8)]], device=latents.device).repeat(B, 1),
+        "aspect_ratio": torch.tensor([[float(h) / float(w)]], device=latents.device).repeat(B, 1),
+    }
+    ts = timestep.to(latents.device).float().expand(B)
+    return model(latents, ts, prompt_embeds, mask=prompt_attention_masks, data_info=data_info, c=c)
+
+
+def generate_sample_1step(model, scheduler, latents, maxt, prompt_embeds, prompt_attention_masks=None, c=None,
+                          use_control: bool = True):
+    """generate.py:22-42: one forward at t = maxt, eps -> x0. With use_control the degraded latent is also the control."""
+    t = torch.full((1,), maxt, device=latents.device).long()
+    if c is None and use_control and getattr(model, "copy_blocks_num", 0) > 0:
+        c = latents
+    out = forward_model(model, latents, t, prompt_embeds, prompt_attention_masks, c=c)
+    return eps_to_mu(scheduler, out, latents, int(maxt))

@@ -1,0 +1,219 @@
+"""process(): the reference's restoration loop (test_scripts/inference.py:56-166) with the same signature, re-scheduled
+for B200: all latent tiles of an image go through the DiT as ONE batch (tiles are independent), the overlap blend is one
+integer-indexed kernel that adds tiles in the reference's loop order (bit-exact masks, fp32 sums in the same order), the
+VAE decodes tiles in batches, and with torch.distributed initialised the tile list is sharded across ranks with two
+all-gathers (tile latents, decoded tiles) -- the only collectives on the path."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .generate import DDPMSchedulerLite, generate_sample_1step
+
+
+def _sliding_windows(h: int, w: int, tile_size: int, tile_stride: int) -> List[Tuple[int, int, int, int]]:
+    """Same integer arithmetic as the reference (test_scripts/inference.py:40-53)."""
+    hi_list = list(range(0, h - tile_size + 1, tile_stride))
+    if (h - tile_size) % tile_stride != 0:
+        hi_list.append(h - tile_size)
+    wi_list = list(range(0, w - tile_size + 1, tile_stride))
+    if (w - tile_size) % tile_stride != 0:
+        wi_list.append(w - tile_size)
+    coords = []
+    for hi in hi_list:
+        for wi in wi_list:
+            coords.append((hi, hi + tile_size, wi, wi + tile_size))
+    return coords
+
+
+# ------------------------------------------------------------------------------------------------ sharding helpers
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of a list of n_items over `world` ranks (first n_items % world ranks get one more)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def all_gather_items(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """local: (n_local, ...) items owned by this rank under shard_range; returns (n_items, ...) in list order on every
+    rank. Pads to equal counts so that a single all_gather_into_tensor (NCCL over NVLink on the GPU box, gloo in the CPU
+    tests) moves everything."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    per = (n_items + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if local.device.type == "cuda":
+        dist.all_gather_into_tensor(out, pad, group=group)
+    else:
+        chunks = list(out.view((world, per) + tuple(local.shape[1:])).unbind(0))
+        dist.all_gather(chunks, pad, group=group)
+    pieces = []
+    for r in range(world):
+        s, e = shard_range(n_items, r, world)
+        pieces.append(out[r * per: r * per + (e - s)])
+    return torch.cat(pieces, dim=0)
+
+
+def _dist_info(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+# ------------------------------------------------------------------------------------------------ kernels' thin wrappers
+def tile_gather(src: torch.Tensor, coords: torch.Tensor, th: int, tw: int, scale: int) -> torch.Tensor:
+    """(N,C,H,W) -> (ntiles,N,C,th,tw); coords int32 (ntiles,2) = (hi, wi) in tile units (x scale)."""
+    N, Cc, H, W = src.shape
+    nt = coords.shape[0]
+    out = torch.empty(nt, N, Cc, th, tw, device=src.device, dtype=torch.float32)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().ir_tile_gather(src.data_ptr(), out.data_ptr(), coords.data_ptr(), nt, N, Cc, H, W, th, tw,
+                                             scale, _lib.stream_ptr()), "ir_tile_gather")
+    return out
+
+
+def tile_blend(tiles: torch.Tensor, coords: torch.Tensor, H: int, W: int, scale: int) -> torch.Tensor:
+    """(ntiles,N,C,th,tw) -> (N,C,H,W): ordered sum of covering tiles / cover count."""
+    nt, N, Cc, th, tw = tiles.shape
+    out = torch.empty(N, Cc, H, W, device=tiles.device, dtype=torch.float32)
+    with torch.cuda.device(tiles.device):
+        _lib.check(_lib.lib().ir_tile_blend(tiles.data_ptr(), coords.data_ptr(), nt, out.data_ptr(), N, Cc, H, W, th,
+                                            tw, scale, _lib.stream_ptr()), "ir_tile_blend")
+    return out
+
+
+def wavelet_reconstruction(content: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+    """utils/image/align_color.py:108-119 on (N,3,H,W) CUDA tensors."""
+    L = _lib.lib()
+    content, style = content.contiguous(), style.contiguous()
+    N, Cc, H, W = content.shape
+    out = torch.empty_like(content)
+    with torch.cuda.device(content.device):
+        ws = torch.empty(L.ir_wavelet_workspace_bytes(N, Cc, H, W), dtype=torch.uint8, device=content.device)
+        _lib.check(L.ir_wavelet_reconstruction(content.data_ptr(), style.data_ptr(), out.data_ptr(), N, Cc, H, W,
+                                               ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "ir_wavelet")
+    return out
+
+
+def adaptive_instance_normalization(content: torch.Tensor, style: torch.Tensor) -> torch.Tensor:
+    """utils/image/align_color.py:44-71 on (N,C,H,W) CUDA tensors."""
+    content, style = content.contiguous(), style.contiguous()
+    N, Cc, H, W = content.shape
+    out = torch.empty_like(content)
+    with torch.cuda.device(content.device):
+        _lib.check(_lib.lib().ir_adain(content.data_ptr(), style.data_ptr(), out.data_ptr(), N, Cc, H * W,
+                                       _lib.stream_ptr()), "ir_adain")
+    return out
+
+
+def to_uint8_nhwc(img: torch.Tensor) -> torch.Tensor:
+    """(N,C,H,W) fp32 -> (N,H,W,C) uint8: clamp(0,1)*255, truncation (test_scripts/inference.py:159-160)."""
+    img = img.contiguous()
+    N, Cc, H, W = img.shape
+    out = torch.empty(N, H, W, Cc, device=img.device, dtype=torch.uint8)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().ir_to_uint8(img.data_ptr(), out.data_ptr(), N, Cc, H, W, _lib.stream_ptr()), "ir_to_uint8")
+    return out
+
+
+_default_scheduler: Optional[DDPMSchedulerLite] = None
+
+
+def _scheduler():
+    global _default_scheduler
+    if _default_scheduler is None:
+        _default_scheduler = DDPMSchedulerLite()
+    return _default_scheduler
+
+
+# ------------------------------------------------------------------------------------------------ restoration core
+@torch.no_grad()
+def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor, y, y_mask, *, tiled: bool,
+                    tile_size: int = 512, tile_stride: int = 448, color_fix_type: str = "wavelet", scheduler=None,
+                    decode_batch: int = 8, group=None, return_latents: bool = False):
+    """Everything of process() between VAE-encode and the uint8 conversion (inference.py:111-153), on the GPU.
+    control: (N,3,H,W) in [0,1]; init_noise: (N,4,H/8,W/8). Returns the fp32 image buffer (N,3,H,W) [and latents]."""
+    scheduler = scheduler or _scheduler()
+    sf = float(vae.config.scaling_factor)
+    n, _, height, width = control.shape
+    h, w = height // 8, width // 8
+    if not tiled:
+        latents = generate_sample_1step(model, scheduler, init_noise, 400, y, y_mask)
+        img = vae.decode_tensor(latents, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
+        return (img, latents) if return_latents else img
+
+    rank, world = _dist_info(group)
+    th = tw = tile_size // 8
+    windows = _sliding_windows(h, w, th, tile_stride // 8)
+    nt = len(windows)
+    coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=control.device)
+    s, e = shard_range(nt, rank, world)
+    mine = coords[s:e].contiguous()
+    # loop 1 (inference.py:128-134): all my tiles as one DiT batch (sample-major inside each tile)
+    if e > s:
+        tiles_in = tile_gather(init_noise.contiguous(), mine, th, tw, 1)              # (k,N,4,th,tw)
+        x0 = generate_sample_1step(model, scheduler, tiles_in.view(-1, 4, th, tw), 400, _tile_captions(y, n, e - s),
+                                   _tile_captions(y_mask, n, e - s))
+        x0 = x0.view(e - s, n, 4, th, tw)
+    else:
+        x0 = torch.empty(0, n, 4, th, tw, device=control.device)
+    if world > 1:
+        x0 = all_gather_items(x0, nt, group)                                          # all-gather #1: tile latents
+    noise_buffer = tile_blend(x0, coords, h, w, 1)                                    # inference.py:133-136
+    # loop 2 (inference.py:139-152): decode + colour-fix my tiles, blend in pixel space
+    outs = []
+    for b0 in range(s, e, max(1, decode_batch)):
+        b1 = min(e, b0 + max(1, decode_batch))
+        cc = coords[b0:b1].contiguous()
+        zt = tile_gather(noise_buffer, cc, th, tw, 1).view(-1, 4, th, tw)
+        ti = vae.decode_tensor(zt, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)   # (k*N,3,8th,8tw)
+        if color_fix_type in ("wavelet", "adain"):
+            cond = tile_gather(control.contiguous(), cc, 8 * th, 8 * tw, 8).view(-1, 3, 8 * th, 8 * tw)
+            ti = wavelet_reconstruction(ti, cond) if color_fix_type == "wavelet" else adaptive_instance_normalization(ti, cond)
+        outs.append(ti.view(b1 - b0, n, 3, 8 * th, 8 * tw))
+    tiles_px = torch.cat(outs, dim=0) if outs else torch.empty(0, n, 3, 8 * th, 8 * tw, device=control.device)
+    if world > 1:
+        tiles_px = all_gather_items(tiles_px, nt, group)                              # all-gather #2: decoded tiles
+    img = tile_blend(tiles_px, coords, height, width, 8)                              # inference.py:151-153
+    return (img, noise_buffer) if return_latents else img
+
+
+def _tile_captions(t, n_samples: int, n_tiles: int):
+    """Captions / masks for a batch laid out (tile, sample): a single caption is shared (K/V computed once)."""
+    if t is None or t.shape[0] == 1:
+        return t
+    return t.repeat((n_tiles,) + (1,) * (t.dim() - 1))
+
+
+@torch.no_grad()
+def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fix_type: str,
+            disable_preprocess_model: bool, tiled: bool, tile_size: int, tile_stride: int, preprocess_model=None,
+            vae=None, y=None, y_mask=None, *, scheduler=None, decode_batch: int = 8, group=None
+            ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """Signature and semantics of the reference's process() (test_scripts/inference.py:56-166).
+    control_imgs: HWC uint8 RGB arrays of equal size (multiples of 64). Returns (preds, stage1_preds) as uint8 HWC."""
+    device = model.device
+    n_samples = len(control_imgs)
+    control = torch.tensor(np.stack(control_imgs) / 255.0, dtype=torch.float32, device=device).clamp_(0, 1)
+    control = control.permute(0, 3, 1, 2).contiguous()
+    if not disable_preprocess_model:
+        if preprocess_model is None:
+            raise ValueError("preprocess_model (SwinIR stage 1) is outside this library; pass one or disable it")
+        control = preprocess_model(control)
+    control_norm = control * 2 - 1
+    c_latent = vae.encode(control_norm).latent_dist.mode().to(torch.float32)
+    init_noise = c_latent * vae.config.scaling_factor
+    img = restore_latents(model, vae, control, init_noise, y, y_mask, tiled=tiled, tile_size=tile_size,
+                          tile_stride=tile_stride, color_fix_type=color_fix_type, scheduler=scheduler,
+                          decode_batch=decode_batch, group=group)
+    x_samples = to_uint8_nhwc(img).cpu().numpy()
+    stage1 = to_uint8_nhwc(control).cpu().numpy()
+    return [x_samples[i] for i in range(n_samples)], [stage1[i] for i in range(n_samples)]
