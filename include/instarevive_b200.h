@@ -47,6 +47,13 @@ const char* ir_version(void);
 /* Kernels launched by this library since load (all threads); bench.py reports the delta as gpu_launches. */
 long long ir_launch_count(void);
 
+/* Per-launch timing of the tensor-core kernels (bench.py roofline pass). Between begin and end every GEMM / conv /
+ * attention launch is bracketed by CUDA events on its stream; end synchronises the device and returns, per class
+ * (0 = tcgen05 GEMM, 1 = tcgen05 implicit-GEMM conv, 2 = attention; arrays of 8), the summed launch durations in ms,
+ * the summed algorithmic FLOPs and the launch counts. Not thread-safe; not for use inside CUDA-graph capture. */
+void ir_profile_begin(void);
+int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launches_by_class);
+
 /* ------------------------------------------------------------------ DiT + ControlNet-Half ---- */
 typedef struct ir_dit ir_dit; /* opaque: packed weights of one (device, model) */
 

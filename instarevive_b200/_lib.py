@@ -30,6 +30,8 @@ PROTOTYPES = {
     "ir_last_error": (C.c_char_p, []),
     "ir_version": (C.c_char_p, []),
     "ir_launch_count": (_ll, []),
+    "ir_profile_begin": (None, []),
+    "ir_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "ir_dit_create": (_i, [C.POINTER(DitConfig), C.POINTER(_vp)]),
     "ir_dit_destroy": (None, [_vp]),
     "ir_dit_num_params": (_i, [_vp]),

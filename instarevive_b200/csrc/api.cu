@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "../../include/instarevive_b200.h"
 #include "dit.cuh"
@@ -22,6 +23,30 @@ void set_last_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+struct ProfRec {
+  cudaEvent_t a, b;
+  int klass;
+  double flops;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static cudaEvent_t g_prof_pending = nullptr;
+
+bool prof_enabled() { return g_prof_on; }
+void prof_before(cudaStream_t s) {
+  cudaEventCreate(&g_prof_pending);
+  cudaEventRecord(g_prof_pending, s);
+}
+void prof_after(cudaStream_t s, int klass, double flops) {
+  ProfRec r;
+  r.a = g_prof_pending;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, s);
+  r.klass = klass;
+  r.flops = flops;
+  g_prof.push_back(r);
+}
+
 }  // namespace ir
 
 using namespace ir;
@@ -38,6 +63,37 @@ extern "C" {
 const char* ir_last_error(void) { return g_err; }
 const char* ir_version(void) { return "instarevive_b200 0.1 (sm_100a)"; }
 long long ir_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void ir_profile_begin(void) {
+  g_prof.clear();
+  g_prof_on = true;
+}
+
+int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launches_by_class) {
+  g_prof_on = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  for (int i = 0; i < PROF_NUM; ++i) {
+    ms_by_class[i] = 0.0;
+    flops_by_class[i] = 0.0;
+    launches_by_class[i] = 0;
+  }
+  for (ProfRec& r : g_prof) {
+    float ms = 0.f;
+    if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.klass >= 0 && r.klass < PROF_NUM) {
+      ms_by_class[r.klass] += ms;
+      flops_by_class[r.klass] += r.flops;
+      launches_by_class[r.klass] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  if (e != cudaSuccess) {
+    set_last_error("ir_profile_end: %s", cudaGetErrorString(e));
+    return IR_ERR_CUDA;
+  }
+  return IR_OK;
+}
 
 int ir_dit_create(const ir_dit_config* cfg, ir_dit** out) {
   if (!cfg || !out) {

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NWARPS * 32) flash_attn_kernel(const AttnDev p
 }
 
 template <int NWARPS>
-static int launch_attn(const AttnDev& p, int B, int heads, cudaStream_t stream) {
+static int launch_attn(const AttnDev& p, int B, int heads, double flops, cudaStream_t stream) {
   constexpr int BQ = NWARPS * 16;
   constexpr int smem = (BQ + 4 * BKV) * LDS * 2;
   auto kern = flash_attn_kernel<NWARPS>;
@@ -244,7 +244,10 @@ static int launch_attn(const AttnDev& p, int B, int heads, cudaStream_t stream) 
     configured = true;
   }
   dim3 grid((p.Tq + BQ - 1) / BQ, heads, B);
+  const bool prof = prof_enabled();
+  if (prof) prof_before(stream);
   kern<<<grid, NWARPS * 32, smem, stream>>>(p);
+  if (prof) prof_after(stream, PROF_ATTN, flops);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;
@@ -271,8 +274,10 @@ int attention_launch(const AttnArgs& a, cudaStream_t stream) {
   p.scale_log2e = a.scale * 1.4426950408889634f;
   // small problems: 64-row CTAs fill the 148 SMs better
   const long ctas128 = (long)((a.Tq + 127) / 128) * a.heads * a.B;
-  if (ctas128 >= 2 * 148) return launch_attn<8>(p, a.B, a.heads, stream);
-  return launch_attn<4>(p, a.B, a.heads, stream);
+  // algorithmic FLOPs: 4 * Tq * Tk * d per (sample, head); Tk is not known on the host for ragged captions (counted 0)
+  const double flops = a.kv_len ? 0.0 : 4.0 * a.B * a.heads * (double)a.Tq * a.Tk * a.head_dim;
+  if (ctas128 >= 2 * 148) return launch_attn<8>(p, a.B, a.heads, flops, stream);
+  return launch_attn<4>(p, a.B, a.heads, flops, stream);
 }
 
 }  // namespace ir

@@ -361,7 +361,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
     configured = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const bool prof = prof_enabled();
+  if (prof) prof_before(stream);
   kern<<<grid, NUM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tw, p);
+  if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch));
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;

@@ -53,4 +53,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 // number of kernel launches issued by this library since load (bench.py's gpu_launches counter)
 void count_launch(int n = 1);
 
+// Optional per-launch timing (bench.py roofline pass): CUDA events around the launches of one kernel class.
+enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_NUM = 8 };
+bool prof_enabled();
+void prof_before(cudaStream_t s);
+void prof_after(cudaStream_t s, int klass, double flops);
+
 }  // namespace ir

@@ -202,7 +202,11 @@ def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fi
     control_imgs: HWC uint8 RGB arrays of equal size (multiples of 64). Returns (preds, stage1_preds) as uint8 HWC."""
     device = model.device
     n_samples = len(control_imgs)
-    control = torch.tensor(np.stack(control_imgs) / 255.0, dtype=torch.float32, device=device).clamp_(0, 1)
+    # reference: torch.tensor(np.stack(imgs) / 255.0, dtype=float32) on the host (inference.py:92); here the uint8 image
+    # is uploaded and divided on the device -- u8/255 in fp32 equals the float64 quotient rounded to fp32 for all 256
+    # values (tests/test_host_logic.py), so `control` is bit-identical
+    host = torch.from_numpy(np.ascontiguousarray(np.stack(control_imgs)))
+    control = host.to(device, non_blocking=True).to(torch.float32).div_(255.0).clamp_(0, 1)
     control = control.permute(0, 3, 1, 2).contiguous()
     if not disable_preprocess_model:
         if preprocess_model is None:
