@@ -210,6 +210,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        const int col = n_blk * BN + c * 32 + col4;
+        const bool col_ok = col < p.N;
+        // Prefetch everything the epilogue reads from global memory BEFORE the TMEM load: the output may alias the
+        // residual (in-place x += ...), so loads issued after the first store could not be hoisted by the compiler.
+        float4 res4[8];
+        float4 gate4[8];
+        uint2 resb[8];
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = row_off[i] >= 0;
+            if (EPI == EPI_F32) {
+              res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              gate4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (ok && p.resid_f32)
+                res4[i] = *reinterpret_cast<const float4*>(p.resid_f32 + (long)b * p.stride_of + row_off[i] * p.ldo_f + col);
+              if (ok && p.gate)
+                gate4[i] = *reinterpret_cast<const float4*>(p.gate + (long)gate_row[i] * p.gate_ld + col);
+            } else if (EPI == EPI_BF16) {
+              resb[i] = make_uint2(0u, 0u);
+              if (ok && p.resid_bf16)
+                resb[i] = *reinterpret_cast<const uint2*>(p.resid_bf16 + (long)b * p.stride_ob + row_off[i] * p.ldo_b + col);
+            }
+          }
+        }
+
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
         tmem_ld_wait();
@@ -227,10 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
 
-        const int col = n_blk * BN + c * 32 + col4;
-        if (col < p.N) {
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
+        if (col_ok) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (row_off[i] < 0) continue;
@@ -240,45 +265,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a.z = a.z * p.alpha + bias4.z;
             a.w = a.w * p.alpha + bias4.w;
             if (EPI == EPI_BF16_GELU) {
-              a.x = gelu_tanh(a.x);
-              a.y = gelu_tanh(a.y);
-              a.z = gelu_tanh(a.z);
-              a.w = gelu_tanh(a.w);
+              a.x = gelu_tanh_fast(a.x);
+              a.y = gelu_tanh_fast(a.y);
+              a.z = gelu_tanh_fast(a.z);
+              a.w = gelu_tanh_fast(a.w);
             }
             if (EPI == EPI_F32) {
               const long o = (long)b * p.stride_of + row_off[i] * p.ldo_f + col;
-              if (p.gate) {
-                const float4 g = *reinterpret_cast<const float4*>(p.gate + (long)gate_row[i] * p.gate_ld + col);
-                a.x *= g.x;
-                a.y *= g.y;
-                a.z *= g.z;
-                a.w *= g.w;
-              }
-              if (p.resid_f32) {
-                const float4 r4 = *reinterpret_cast<const float4*>(p.resid_f32 + o);
-                a.x += r4.x;
-                a.y += r4.y;
-                a.z += r4.z;
-                a.w += r4.w;
-              }
+              a.x = a.x * gate4[i].x + res4[i].x;
+              a.y = a.y * gate4[i].y + res4[i].y;
+              a.z = a.z * gate4[i].z + res4[i].z;
+              a.w = a.w * gate4[i].w + res4[i].w;
               *reinterpret_cast<float4*>(p.out_f32 + o) = a;
               if (p.out_bf16) {
                 const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
-                uint2 u = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-                *reinterpret_cast<uint2*>(p.out_bf16 + ob) = u;
+                *reinterpret_cast<uint2*>(p.out_bf16 + ob) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
               }
             } else {
               const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
-              if (EPI == EPI_BF16 && p.resid_bf16) {
-                const uint2 ru = *reinterpret_cast<const uint2*>(p.resid_bf16 + ob);
-                const float2 r0 = unpack_bf16x2(ru.x), r1 = unpack_bf16x2(ru.y);
+              if (EPI == EPI_BF16) {
+                const float2 r0 = unpack_bf16x2(resb[i].x), r1 = unpack_bf16x2(resb[i].y);
                 a.x += r0.x;
                 a.y += r0.y;
                 a.z += r1.x;
                 a.w += r1.y;
               }
-              uint2 u = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-              *reinterpret_cast<uint2*>(p.out_bf16 + ob) = u;
+              *reinterpret_cast<uint2*>(p.out_bf16 + ob) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
             }
           }
         }
@@ -393,12 +405,15 @@ static int pick_bn(long m_tiles, int N, int forced) {
   int best = 128;
   double best_cost = 1e30;
   const int cands[3] = {256, 128, 64};
+  // relative cost of one tile per K-block, calibrated on B200 (8192^3: BN 256 / 128 / 64 -> 1334 / 809 / 495 TFLOP/s:
+  // narrower tiles are shared-memory-bandwidth bound on the A operand); +15 % of a tile for the exposed last epilogue
+  const double tile_cost[3] = {256.0, 206.0, 168.0};
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn > 64 && N <= bn / 2) continue;  // tile mostly empty
     const long tiles = m_tiles * ((N + bn - 1) / bn);
     const long waves = (tiles + sms - 1) / sms;
-    const double cost = (double)waves * (bn + 32);
+    const double cost = ((double)waves + 0.15) * tile_cost[i];
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = bn;

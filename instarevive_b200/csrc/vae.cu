@@ -76,14 +76,26 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   const int p0 = chunk * chunk_px;
   const int p1 = min(P, p0 + chunk_px);
   float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
-  for (int p = p0 + ps; p < p1; p += pps) {
-    const uint4 u = *reinterpret_cast<const uint4*>(x + ((long)n * P + p) * C + cs * 8);
+  const bf16* xb = x + (long)n * P * C + cs * 8;
+  auto accum = [&](const uint4& u) {
     const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     s_lo += (a.x + a.y) + (b.x + b.y);
     q_lo += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
     s_hi += (c.x + c.y) + (d.x + d.y);
     q_hi += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+  };
+  int p = p0 + ps;
+  for (; p + 3 * pps < p1; p += 4 * pps) {  // 4 independent 16 B loads in flight per thread
+    const uint4 u0 = *reinterpret_cast<const uint4*>(xb + (long)p * C);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(xb + (long)(p + pps) * C);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(xb + (long)(p + 2 * pps) * C);
+    const uint4 u3 = *reinterpret_cast<const uint4*>(xb + (long)(p + 3 * pps) * C);
+    accum(u0);
+    accum(u1);
+    accum(u2);
+    accum(u3);
   }
+  for (; p < p1; p += pps) accum(*reinterpret_cast<const uint4*>(xb + (long)p * C));
   sm[threadIdx.x][0] = s_lo;
   sm[threadIdx.x][1] = q_lo;
   sm[threadIdx.x][2] = s_hi;
@@ -109,21 +121,34 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   }
 }
 
-// Stage 2: (mean, rstd) per (image, group); chunk partials are summed in index order in double precision.
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,
-                                   double inv_count, float eps) {
-  const int n = blockIdx.x, g = threadIdx.x;
-  double s = 0.0, q = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    const float* pp = partial + (((long)n * nchunks + c) * 32 + g) * 2;
-    s += (double)pp[0];
-    q += (double)pp[1];
+// Stage 2: (mean, rstd) per (image, group). One block per image, 8 warps x 4 groups; lanes stride over the chunk
+// partials and are combined by a fixed shuffle tree in double precision (deterministic).
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats,
+                                                          int nchunks, double inv_count, float eps) {
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int g = warp * 4 + k;
+    double s = 0.0, q = 0.0;
+    for (int c = lane; c < nchunks; c += 32) {
+      const float2 pp = *reinterpret_cast<const float2*>(partial + (((long)n * nchunks + c) * 32 + g) * 2);
+      s += (double)pp.x;
+      q += (double)pp.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double mean = s * inv_count;
+      double var = q * inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((long)n * 32 + g) * 2] = (float)mean;
+      stats[((long)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
-  const double mean = s * inv_count;
-  double var = q * inv_count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[((long)n * 32 + g) * 2] = (float)mean;
-  stats[((long)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // Stage 3: y = act((x - mean) * rstd * gamma + beta) -> bf16; act = SiLU (x * sigmoid(x), model.py:43-45) or none.
@@ -131,24 +156,21 @@ template <bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long total_vec, int P, int C) {
-  const int tpp = C / 8;
+  const int tpp = C / 8;   // 16-byte vectors per pixel; divides the block size, so a thread keeps its channel slot
   const int cpg = C / 32;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total_vec; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % tpp) * 8;
-    const long pix = i / tpp;
-    const int n = (int)(pix / P);
-    const uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
-    float v[8];
-    {
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-    }
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + c0 / cpg) * 2);
-    const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + (c0 + 4) / cpg) * 2);
+  const int c0 = (threadIdx.x % tpp) * 8;
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+  const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int g_lo = c0 / cpg, g_hi = (c0 + 4) / cpg;
+  const long stride = (long)gridDim.x * blockDim.x;
+  auto one = [&](long i, const uint4& u) {
+    const int n = (int)((i / tpp) / P);
+    const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_lo) * 2);
+    const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_hi) * 2);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float2 st = k < 4 ? st_lo : st_hi;
@@ -158,7 +180,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     }
     *reinterpret_cast<uint4*>(y + i * 8) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  };
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total_vec; i += 4 * stride) {
+    const uint4 u0 = *reinterpret_cast<const uint4*>(x + i * 8);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(x + (i + stride) * 8);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(x + (i + 2 * stride) * 8);
+    const uint4 u3 = *reinterpret_cast<const uint4*>(x + (i + 3 * stride) * 8);
+    one(i, u0);
+    one(i + stride, u1);
+    one(i + 2 * stride, u2);
+    one(i + 3 * stride, u3);
   }
+  for (; i < total_vec; i += stride) one(i, *reinterpret_cast<const uint4*>(x + i * 8));
 }
 
 // ------------------------------------------------------------------------------------------------ upsample
@@ -505,7 +539,7 @@ static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
   IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
   gn_partial_kernel<<<dim3(nchunks, c.B), 256, 0, c.s>>>(x, c.w.partial, P, C, chunk_px, nchunks);
   IR_CUDA_CHECK(cudaGetLastError());
-  gn_finalize_kernel<<<c.B, 32, 0, c.s>>>(c.w.partial, c.w.stats, nchunks, 1.0 / ((double)P * (C / 32)), 1e-6f);
+  gn_finalize_kernel<<<c.B, 256, 0, c.s>>>(c.w.partial, c.w.stats, nchunks, 1.0 / ((double)P * (C / 32)), 1e-6f);
   IR_CUDA_CHECK(cudaGetLastError());
   const long total_vec = (long)c.B * P * C / 8;
   int grid = div_up_l(total_vec, 256);
