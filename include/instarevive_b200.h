@@ -150,6 +150,13 @@ int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int 
 int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldk,
                       long long ldv, long long ldo, int B, int heads, int head_dim, int Tq, int Tk,
                       const int32_t* kv_off, const int32_t* kv_len, float scale, void* stream);
+/* qkv projection with the head-major scatter epilogue: A (M,K) bf16, W (3*H*hd, K) bf16 ->
+ * q, k: [M/T][H][T][hd] bf16, vt: [M/T][H][hd][Tp] bf16. */
+int ir_gemm_qkv_heads(const void* A, const void* W, const float* bias, int M, int K, int T, int Tp, int H, int hd,
+                      void* q_heads, void* k_heads, void* vt_heads, int force_bn, void* stream);
+/* tcgen05 self-attention on head-major operands (see ir_gemm_qkv_heads); out: (B*T, ldo) bf16. */
+int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* vt_heads, void* out, long long ldo, int B,
+                         int H, int head_dim, int T, int Tp, float scale, void* stream);
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream);
 int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream);

@@ -367,6 +367,46 @@ int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, lo
   return attention_launch(a, (cudaStream_t)stream);
 }
 
+int ir_gemm_qkv_heads(const void* A, const void* W, const float* bias, int M, int K, int T, int Tp, int H, int hd,
+                      void* q_heads, void* k_heads, void* vt_heads, int force_bn, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)A;
+  g.lda = K;
+  g.W = (const bf16*)W;
+  g.ldw = K;
+  g.M = M;
+  g.N = 3 * H * hd;
+  g.K = K;
+  g.epi = EPI_QKV;
+  g.bias = bias;
+  g.q_heads = (bf16*)q_heads;
+  g.k_heads = (bf16*)k_heads;
+  g.vt_heads = (bf16*)vt_heads;
+  g.qkv_T = T;
+  g.qkv_Tp = Tp;
+  g.qkv_H = H;
+  g.qkv_hd = hd;
+  g.force_bn = force_bn;
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
+int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* vt_heads, void* out, long long ldo, int B,
+                         int H, int head_dim, int T, int Tp, float scale, void* stream) {
+  AttnTcArgs a;
+  a.q = (const bf16*)q_heads;
+  a.k = (const bf16*)k_heads;
+  a.vt = (const bf16*)vt_heads;
+  a.out = (bf16*)out;
+  a.ldo = ldo;
+  a.B = B;
+  a.H = H;
+  a.head_dim = head_dim;
+  a.T = T;
+  a.Tp = Tp;
+  a.scale = scale;
+  return attention_tc_launch(a, (cudaStream_t)stream);
+}
+
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream) {
   return ln_modulate_launch(x, (bf16*)out_bf16, shift, scale, mod_stride, rows, T, D, (cudaStream_t)stream);

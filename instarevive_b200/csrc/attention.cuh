@@ -20,4 +20,17 @@ struct AttnArgs {
 
 int attention_launch(const AttnArgs& a, cudaStream_t stream);
 
+// tcgen05 self-attention on head-major operands produced by the qkv GEMM (EPI_QKV):
+// q, k: [B][H][T][head_dim] bf16; vt: [B][H][head_dim][Tp] bf16 (V transposed); out: [B*T][ldo] bf16, head-interleaved.
+struct AttnTcArgs {
+  const bf16* q = nullptr;
+  const bf16* k = nullptr;
+  const bf16* vt = nullptr;
+  bf16* out = nullptr;
+  long ldo = 0;
+  int B = 0, H = 0, head_dim = 0, T = 0, Tp = 0;
+  float scale = 1.0f;
+};
+int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream);
+
 }  // namespace ir

@@ -4,6 +4,7 @@
 #include "dit.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ir {
@@ -220,6 +221,7 @@ struct DitWs {
   float *xs, *cs;                 // fp32 residual streams (base, control)
   bf16 *xq, *cb;                  // bf16 copies (cross-attn query input / control stream for after_proj)
   bf16 *xn, *qkv, *att, *qc, *hm; // per-block scratch
+  bf16 *qh, *kh, *vt;             // head-major q / k and transposed v for the tcgen05 attention kernel
   bf16* ctok;                     // patch-embedded control tokens (bf16, before_proj input)
   float *sin, *hid, *t, *t0, *mod;
   bf16 *yg, *yh, *ye;
@@ -236,6 +238,9 @@ static size_t carve(const Dit* d, DitWs& w, void* base, int B, int H, int W, int
   w.ctok = b.take<bf16>(M * D);
   w.xn = b.take<bf16>(M * D);
   w.qkv = b.take<bf16>(M * 3 * D);
+  w.qh = b.take<bf16>(M * D);
+  w.kh = b.take<bf16>(M * D);
+  w.vt = b.take<bf16>((long)B * D * (((H / 2) * (W / 2) + 7) / 8 * 8));
   w.att = b.take<bf16>(M * D);
   w.qc = b.take<bf16>(M * D);
   w.hm = b.take<bf16>(M * Dm);
@@ -286,13 +291,27 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
 
   // x = x + gate_msa * attn(modulate(norm1(x)))
   IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 0 * D, mod + 1 * D, 6 * D, M, T, D, c.s));
-  {
+  static const bool legacy_attn = [] {
+    const char* e = getenv("IR_ATTN_LEGACY");  // debugging aid: A/B against the mma.sync kernel
+    return e && e[0] == '1';
+  }();
+  if (!legacy_attn) {
+    const int H = d->cfg.heads, hd = D / H, Tp = (T + 7) / 8 * 8;
+    GemmArgs g;
+    g.A = c.w.xn; g.lda = D; g.W = w.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+    g.epi = EPI_QKV; g.bias = w.b_qkv;
+    g.q_heads = c.w.qh; g.k_heads = c.w.kh; g.vt_heads = c.w.vt;
+    g.qkv_T = T; g.qkv_Tp = Tp; g.qkv_H = H; g.qkv_hd = hd;
+    IR_TRY(gemm_launch(g, c.s));
+    AttnTcArgs a;
+    a.q = c.w.qh; a.k = c.w.kh; a.vt = c.w.vt; a.out = c.w.att; a.ldo = D;
+    a.B = c.B; a.H = H; a.head_dim = hd; a.T = T; a.Tp = Tp; a.scale = attn_scale;
+    IR_TRY(attention_tc_launch(a, c.s));
+  } else {
     GemmArgs g;
     g.A = c.w.xn; g.lda = D; g.W = w.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
     g.epi = EPI_BF16; g.bias = w.b_qkv; g.out_bf16 = c.w.qkv; g.ldo_b = 3 * D;
     IR_TRY(gemm_launch(g, c.s));
-  }
-  {
     AttnArgs a;
     a.q = c.w.qkv; a.k = c.w.qkv + D; a.v = c.w.qkv + 2 * D; a.out = c.w.att;
     a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;

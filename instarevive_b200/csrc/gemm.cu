@@ -56,6 +56,9 @@ struct GemmDev {
   const float* gate;
   long gate_ld;
   int rows_per_gate;
+  // EPI_QKV
+  bf16 *q_heads, *k_heads, *vt_heads;
+  int qkv_T, qkv_Tp, qkv_H, qkv_hd;
 };
 
 template <int BN, int EPI, bool CONV>
@@ -210,6 +213,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        if (EPI == EPI_QKV) {
+          // head-major scatter of the qkv projection; D1 = H*hd is a multiple of 32, so a chunk is all-q, all-k or all-v
+          const int D1 = p.qkv_H * p.qkv_hd;
+          const int cbase = n_blk * BN + c * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
+          tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          }
+          if (cbase >= p.N) continue;
+          const int which = cbase / D1;
+          if (which == 2) {
+            // v is stored transposed ([b][head][d][t]): stage the 32 x 32 chunk, then lane = channel reads its
+            // column (conflict-free) and writes 32 consecutive tokens = 64 contiguous bytes
+            const int gm0 = m_blk * BM + q * 32;
+            const int bb0 = gm0 / p.qkv_T, t0 = gm0 - bb0 * p.qkv_T;
+            const bool fast = (gm0 + 32 <= p.M) && (t0 + 32 <= p.qkv_T) && ((t0 & 7) == 0) && ((p.qkv_Tp & 7) == 0);
+            if (fast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+              }
+              __syncwarp();
+              const int cl = cbase + lane - 2 * D1;
+              const int head = cl / p.qkv_hd, d = cl - head * p.qkv_hd;
+              const float bv = p.bias[cbase + lane];
+              bf16* dst = p.vt_heads + (((long)bb0 * p.qkv_H + head) * p.qkv_hd + d) * p.qkv_Tp + t0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = stg[(g * 8 + i) * STG_LD + lane] + bv;
+                *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                                                                    pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+              }
+              __syncwarp();
+            } else {
+              const int gm = gm0 + lane;
+              if (gm < p.M) {
+                const int bb = gm / p.qkv_T, t = gm - bb * p.qkv_T;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int cl = cbase + j - 2 * D1;
+                  const int head = cl / p.qkv_hd, d = cl - head * p.qkv_hd;
+                  const float val = __uint_as_float(v[j]) + p.bias[cbase + j];
+                  p.vt_heads[(((long)bb * p.qkv_H + head) * p.qkv_hd + d) * p.qkv_Tp + t] = __float2bfloat16(val);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+            }
+            __syncwarp();
+            const int cl = cbase + col4 - which * D1;
+            const int head = cl / p.qkv_hd, d = cl - head * p.qkv_hd;
+            const float4 bias4 = *reinterpret_cast<const float4*>(p.bias + cbase + col4);
+            bf16* dst = which == 0 ? p.q_heads : p.k_heads;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (row_off[i] < 0) continue;
+              const int gm = (int)row_off[i];
+              const int bb = gm / p.qkv_T, t = gm - bb * p.qkv_T;
+              float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * STG_LD + col4);
+              *reinterpret_cast<uint2*>(dst + (((long)bb * p.qkv_H + head) * p.qkv_T + t) * p.qkv_hd + d) =
+                  make_uint2(pack_bf16x2(a.x + bias4.x, a.y + bias4.y), pack_bf16x2(a.z + bias4.z, a.w + bias4.w));
+            }
+            __syncwarp();
+          }
+          continue;
+        }
         const int col = n_blk * BN + c * 32 + col4;
         const bool col_ok = col < p.N;
         // Prefetch everything the epilogue reads from global memory BEFORE the TMEM load: the output may alias the
@@ -325,8 +407,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor map, innermost dimension first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
@@ -342,7 +424,8 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu,%llu,%llu base %p)", (int)r, rank,
@@ -351,6 +434,11 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     return IR_ERR_DRIVER;
   }
   return IR_OK;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return make_tensor_map(m, base, rank, dims, strides_bytes, box, 128);
 }
 
 static int g_num_sms = 0;
@@ -363,6 +451,8 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+
+int device_num_sms() { return num_sms(); }
 
 template <int BN, int EPI, bool CONV>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
@@ -388,6 +478,9 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, con
     case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV>(ta, tw, p, s);
     case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV>(ta, tw, p, s);
     case EPI_F32: return launch_inst<BN, EPI_F32, CONV>(ta, tw, p, s);
+    case EPI_QKV:
+      if (!CONV) return launch_inst<BN, EPI_QKV, false>(ta, tw, p, s);
+      break;
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return IR_ERR_INVALID;
@@ -429,7 +522,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.N % 4 == 0, "gemm: N=%d must be a multiple of 4", a.N);
   IR_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
              "gemm: operands must be 16-byte aligned");
-  if (a.epi == EPI_F32) {
+  if (a.epi == EPI_QKV) {
+    IR_REQUIRE(a.q_heads && a.k_heads && a.vt_heads && a.bias && !a.conv && a.batch == 1, "gemm: EPI_QKV needs q/k/vt outputs and a bias");
+    IR_REQUIRE(a.qkv_hd % 4 == 0 && (a.qkv_H * a.qkv_hd) % 32 == 0 && a.N == 3 * a.qkv_H * a.qkv_hd && a.qkv_T > 0 &&
+                   a.M % a.qkv_T == 0 && a.qkv_Tp >= a.qkv_T,
+               "gemm: EPI_QKV shape mismatch");
+  } else if (a.epi == EPI_F32) {
     IR_REQUIRE(a.out_f32 && a.ldo_f % 4 == 0, "gemm: EPI_F32 needs out_f32 with ld %% 4 == 0");
     IR_REQUIRE(!a.out_bf16 || a.ldo_b % 4 == 0, "gemm: bf16 copy needs ld %% 4 == 0");
   } else {
@@ -457,6 +555,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.gate = a.gate;
   p.gate_ld = a.gate_ld;
   p.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1;
+  p.q_heads = a.q_heads;
+  p.k_heads = a.k_heads;
+  p.vt_heads = a.vt_heads;
+  p.qkv_T = a.qkv_T;
+  p.qkv_Tp = a.qkv_Tp;
+  p.qkv_H = a.qkv_H;
+  p.qkv_hd = a.qkv_hd;
 
   CUtensorMap ta, tw;
   long m_tiles;

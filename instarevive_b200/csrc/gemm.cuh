@@ -8,6 +8,8 @@ enum GemmEpilogue {
   EPI_BF16 = 0,       // out_bf16 = alpha*acc + bias (+ resid_bf16)
   EPI_BF16_GELU = 1,  // out_bf16 = gelu_tanh(alpha*acc + bias)
   EPI_F32 = 2,        // out_f32 = resid_f32 + gate * (alpha*acc + bias); optional bf16 copy of out_f32
+  EPI_QKV = 3,        // attn.qkv projection scattered head-major for the tcgen05 attention kernel:
+                      //   q, k -> [B][H][T][hd] bf16, v -> transposed [B][H][hd][Tp] bf16 (acc + bias)
 };
 
 // C[b][m][n] = sum_k A[b][m][k] * W[b][n][k]   (both operands K-major bf16, fp32 accumulation in TMEM).
@@ -45,8 +47,20 @@ struct GemmArgs {
   long gate_ld = 0;
   int rows_per_gate = 1;
 
+  // EPI_QKV only: N = 3*H*hd, rows are (b, t) with T tokens per sample
+  bf16* q_heads = nullptr;
+  bf16* k_heads = nullptr;
+  bf16* vt_heads = nullptr;
+  int qkv_T = 0, qkv_Tp = 0, qkv_H = 0, qkv_hd = 0;
+
   int force_bn = 0;  // 0 = heuristic; otherwise 64 / 128 / 256
 };
+
+// bf16 tiled tensor map (innermost dimension first; strides in bytes for dims 1..rank-1; zero OOB fill).
+// swizzle_bytes: 128 or 32 (the inner box extent must equal it).
+int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes);
+int device_num_sms();
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 

@@ -161,6 +161,39 @@ def attn_case(B, T, heads=16, hd=72, cross_lens=None):
         report(f"cross-attn B{B} T{T} lens{cross_lens}", out, torch.cat(refs), 1e-2)
 
 
+def attn_tc_case(B, T, heads=16, hd=72):
+    """EPI_QKV GEMM (head-major scatter) + tcgen05 attention vs torch SDPA on the same bf16 q/k/v."""
+    g = torch.Generator(device="cpu").manual_seed(B * 13 + T)
+    D = heads * hd
+    M = B * T
+    Tp = (T + 7) // 8 * 8
+    A = (torch.randn(M, D, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(3 * D, D, generator=g) * 0.03).to(dev).bfloat16()
+    bias = (torch.randn(3 * D, generator=g) * 0.1).to(dev)
+    qh = torch.zeros(B, heads, T, hd, device=dev, dtype=torch.bfloat16)
+    kh = torch.zeros_like(qh)
+    vt = torch.zeros(B, heads, hd, Tp, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_gemm_qkv_heads(P(A), P(W), P(bias), M, D, T, Tp, heads, hd, P(qh), P(kh), P(vt), 0, S()), "qkv heads")
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t() + bias).view(B, T, 3, heads, hd)
+    report(f"qkv-heads q B{B} T{T}", qh, ref[:, :, 0].permute(0, 2, 1, 3), 1e-2)
+    report(f"qkv-heads k B{B} T{T}", kh, ref[:, :, 1].permute(0, 2, 1, 3), 1e-2)
+    report(f"qkv-heads vt B{B} T{T}", vt[..., :T], ref[:, :, 2].permute(0, 2, 3, 1), 1e-2)
+    out = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_attention_tc_bf16(P(qh), P(kh), P(vt), P(out), D, B, heads, hd, T, Tp, hd ** -0.5, S()), "attention_tc")
+    torch.cuda.synchronize()
+    q, k, v = qh.float(), kh.float(), vt[..., :T].float().transpose(2, 3)
+    sref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(M, D)
+    report(f"attn-tc B{B} T{T}", out, sref, 1e-2)
+    # d truncated to 64: what the result would be if the 16-column remainder k-step were ignored (bisecting aid)
+    s64 = F.scaled_dot_product_attention(q[..., :64], k[..., :64], v, scale=hd ** -0.5).permute(0, 2, 1, 3).reshape(M, D)
+    print(f"      (vs d-truncated-to-64 reference: {(out.float() - s64).abs().max().item():.4g})", flush=True)
+    ms = time_ms(lambda: L.ir_attention_tc_bf16(P(qh), P(kh), P(vt), P(out), D, B, heads, hd, T, Tp, hd ** -0.5, S()))
+    print(f"[perf] attn-tc B{B} T{T}: {ms * 1e3:.1f} us {4.0 * B * heads * T * T * hd / ms / 1e9:.1f} TFLOP/s", flush=True)
+    ms = time_ms(lambda: L.ir_gemm_qkv_heads(P(A), P(W), P(bias), M, D, T, Tp, heads, hd, P(qh), P(kh), P(vt), 0, S()))
+    print(f"[perf] qkv-heads gemm M{M}: {ms * 1e3:.1f} us {2.0 * M * 3 * D * D / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def ln_case(B, T, D=1152):
     g = torch.Generator(device="cpu").manual_seed(5)
     x = (torch.randn(B * T, D, generator=g) * 3 + 1).to(dev)
@@ -176,7 +209,7 @@ def ln_case(B, T, D=1152):
 
 def main():
     print(torch.cuda.get_device_name(0), L.ir_version().decode(), flush=True)
-    which = sys.argv[1:] or ["gemm", "conv", "attn", "ln", "perf"]
+    which = sys.argv[1:] or ["gemm", "conv", "attn", "attn_tc", "ln", "perf"]
     if "gemm" in which:
         for bn in (64, 128, 256):
             gemm_case(256, 256, 128, 0, bn)
@@ -199,6 +232,12 @@ def main():
         attn_case(1, 4096)
         attn_case(2, 1024, cross_lens=[120, 77])
         attn_case(3, 600, cross_lens=[1, 300, 64])
+    if "attn_tc" in which:
+        attn_tc_case(1, 256)
+        attn_tc_case(1, 1024)
+        attn_tc_case(2, 1000)
+        attn_tc_case(1, 4096)
+        attn_tc_case(3, 1296)
     if "ln" in which:
         ln_case(2, 1024)
     if "perf" in which:
