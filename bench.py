@@ -230,6 +230,12 @@ def run_cuda(args):
     clk = clocks.stop()
     value = mp_per_step * args.steps / (total_ms / 1e3)
 
+    # checksum of one restored image (tiled workload: must be identical for every world size -- bit-exact sharding)
+    import zlib
+    chk_img = step_resident()
+    torch.cuda.synchronize()
+    checksum = zlib.crc32(pipeline.to_uint8_nhwc(chk_img).cpu().numpy().tobytes())
+
     # one extra resident step inside a cudaProfilerStart/Stop range (outside every timed region) so that the same
     # command can be profiled with `ncu --profile-from-start off` (profiles/README.md)
     torch.cuda.synchronize()
@@ -296,7 +302,7 @@ def run_cuda(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "instarevive_b200.process(model, [uint8 HWC image], ...)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
-            "model_tflops_per_step": flops_step / 1e12 if flops_step else None,
+            "model_tflops_per_step": flops_step / 1e12 if flops_step else None, "output_crc32": checksum,
             "mfu_vs_measured_peak": (flops_step / (total_ms / args.steps / 1e3) / 1e12 / peak_tf) if flops_step else None,
         }
         print(json.dumps(line), flush=True)

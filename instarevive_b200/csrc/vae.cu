@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     for (int k = 0; k < 8; ++k) {
       const float2 st = k < 4 ? st_lo : st_hi;
       float t = (v[k] - st.x) * st.y * gm[k] + bt[k];
-      if (SILU) t = t / (1.0f + __expf(-t));
+      if (SILU) t = silu_fast(t);
       v[k] = t;
     }
     *reinterpret_cast<uint4*>(y + i * 8) =
@@ -533,8 +533,10 @@ static const T* vp(const Vae* v, const std::string& name) {
 // y = act(GroupNorm(x)); x, y: (B, P, C) NHWC bf16
 static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, int P, int C, bool silu_act) {
   IR_REQUIRE(C % 32 == 0 && (C / 32 == 4 || C / 32 == 8 || C / 32 == 16), "group_norm: C=%d unsupported", C);
+  // The chunking must depend on the image size only (never on the batch): the fp32 partial sums are then grouped
+  // identically however tiles are batched or sharded across GPUs, which keeps tiled restoration bit-reproducible.
   int chunk_px = 256;
-  while (div_up_l(P, chunk_px) * (long)c.B > 1184 && chunk_px < (1 << 20)) chunk_px *= 2;
+  while (div_up_l(P, chunk_px) > 1024) chunk_px *= 2;
   const int nchunks = div_up_l(P, chunk_px);
   IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
   gn_partial_kernel<<<dim3(nchunks, c.B), 256, 0, c.s>>>(x, c.w.partial, P, C, chunk_px, nchunks);

@@ -138,7 +138,7 @@ def _scheduler():
 @torch.no_grad()
 def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor, y, y_mask, *, tiled: bool,
                     tile_size: int = 512, tile_stride: int = 448, color_fix_type: str = "wavelet", scheduler=None,
-                    decode_batch: int = 8, group=None, return_latents: bool = False):
+                    decode_batch: int = 8, group=None, return_latents: bool = False, distributed: bool = True):
     """Everything of process() between VAE-encode and the uint8 conversion (inference.py:111-153), on the GPU.
     control: (N,3,H,W) in [0,1]; init_noise: (N,4,H/8,W/8). Returns the fp32 image buffer (N,3,H,W) [and latents]."""
     scheduler = scheduler or _scheduler()
@@ -150,7 +150,7 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
         img = vae.decode_tensor(latents, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
         return (img, latents) if return_latents else img
 
-    rank, world = _dist_info(group)
+    rank, world = _dist_info(group) if distributed else (0, 1)
     th = tw = tile_size // 8
     windows = _sliding_windows(h, w, th, tile_stride // 8)
     nt = len(windows)

@@ -162,17 +162,22 @@ def make_inputs(B: int, h: int, w: int, seed: int = 0, lmax: int = 120, lens=(77
 
 # ---------------------------------------------------------------------------------------------- synthetic images / encoder
 def synthetic_degraded_image(height: int, width: int, seed: int = 0):
-    """uint8 RGB "degraded image" of SURVEY 8d: uniform noise, 3x box blur, sigma=10 gaussian noise, clamp."""
+    """uint8 RGB "degraded image" of SURVEY 8d: uniform noise, 3x box blur, sigma=10 gaussian noise, clamp.
+    Pure single-threaded numpy in float64 with a fixed summation order, so the image is bit-identical on every host
+    and for every OpenMP thread count (torchrun sets OMP_NUM_THREADS=1)."""
     import numpy as np
     rs = np.random.RandomState(seed)
-    img = rs.randint(0, 256, size=(height, width, 3)).astype(np.float32)
-    t = torch.from_numpy(img).permute(2, 0, 1)[None]
-    k = torch.ones(3, 1, 5, 5) / 25.0
+    img = rs.randint(0, 256, size=(height, width, 3)).astype(np.float64)
     for _ in range(3):
-        t = torch.nn.functional.conv2d(torch.nn.functional.pad(t, (2, 2, 2, 2), mode="reflect"), k, groups=3)
-    t = (t - t.mean()) * 6.0 + 128.0  # restore contrast lost to the blur
-    t = t + torch.from_numpy(rs.randn(*t.shape).astype(np.float32)) * 10.0
-    return t.clamp(0, 255)[0].permute(1, 2, 0).numpy().astype(np.uint8)
+        p = np.pad(img, ((2, 2), (2, 2), (0, 0)), mode="reflect")
+        acc = np.zeros_like(img)
+        for dy in range(5):
+            for dx in range(5):
+                acc += p[dy:dy + height, dx:dx + width]
+        img = acc / 25.0
+    img = (img - img.mean()) * 6.0 + 128.0  # restore contrast lost to the blur
+    img = img + rs.randn(height, width, 3) * 10.0
+    return np.clip(img, 0, 255).astype(np.uint8)
 
 
 class SyntheticVAE:

@@ -238,5 +238,9 @@ def test_tiled_restore_sharding_is_bit_identical(vae_dec):
         parts.append(ir.generate_sample_1step(net, sched, tin.view(-1, 4, 64, 64), 400, y, mask).view(e - s, 1, 4, 64, 64))
     lat2 = pipeline.tile_blend(torch.cat(parts), coords, 128, 128, 1)
     assert torch.equal(lat2, lat)
+    # pixel space: decoding the tiles in differently sized batches (what differently sized shards do) is bit-identical
+    full3 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=3)
+    full1 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=1)
+    assert torch.equal(full3, full) and torch.equal(full1, full)
     assert full.shape == (1, 3, H, W) and torch.isfinite(full).all()
     assert float(full.min()) > -0.5 and float(full.max()) < 1.5
