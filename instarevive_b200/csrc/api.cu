@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -22,6 +23,13 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("IR_NO_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 
 struct ProfRec {
   cudaEvent_t a, b;

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(NWARPS * 32) flash_attn_kernel(const AttnDev p
   const int head = blockIdx.y;
   const int b = blockIdx.z;
 
+  pdl_wait();
+  pdl_launch();
   const int kv_start = p.kv_off ? p.kv_off[b] : b * p.Tk;
   const int kv_n = p.kv_len ? p.kv_len[b] : p.Tk;
   const int n_tiles = (kv_n + BKV - 1) / BKV;
@@ -246,7 +248,7 @@ static int launch_attn(const AttnDev& p, int B, int heads, double flops, cudaStr
   dim3 grid((p.Tq + BQ - 1) / BQ, heads, B);
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  kern<<<grid, NWARPS * 32, smem, stream>>>(p);
+  IR_CUDA_CHECK(launch_pdl(kern, grid, dim3(NWARPS * 32), smem, stream, p));
   if (prof) prof_after(stream, PROF_ATTN, flops);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -102,6 +102,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -339,7 +341,7 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   dim3 grid((a.T + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  attn_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(mq64, mq16, mk64, mk16, mvt, p);
+  IR_CUDA_CHECK(launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mq64, mq16, mk64, mk16, mvt, p));
   if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -96,6 +96,13 @@ IR_DEVINL float silu_fast(float x) {
   return x * (0.5f * t + 0.5f);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor is still
+// draining; it must execute pdl_wait() before its first global-memory access that depends on (or could overwrite data
+// of) the predecessor. pdl_launch() lets the successor's CTAs be scheduled as SMs free up.
+IR_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+IR_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 IR_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -202,6 +202,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   constexpr int D = V * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch();
   if (row >= rows) return;
   const float* xr = x + (long)row * D;
   float4 v[V];
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
 int ln_modulate_launch(const float* x, bf16* out, const float* shift, const float* scale, long mod_stride, int rows,
                        int T, int D, cudaStream_t s) {
   IR_REQUIRE(D == 1152, "ln_modulate: hidden size %d unsupported (kernel is specialised for 1152)", D);
-  ln_modulate_kernel<9><<<div_up(rows, 8), 256, 0, s>>>(x, out, shift, scale, mod_stride, rows, T);
+  IR_CUDA_CHECK(launch_pdl(ln_modulate_kernel<9>, dim3(div_up(rows, 8)), dim3(256), 0, s, x, out, shift, scale, mod_stride, rows, T));
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;

@@ -105,6 +105,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_launch();
 
   const int mb_total = p.m_blocks * p.batch;
 
@@ -465,7 +468,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  kern<<<grid, NUM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ta, tw, p);
+  IR_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), GemmCfg<BN>::SMEM_BYTES, stream, ta, tw, p));
   if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch));
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -62,6 +62,23 @@ int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
                     const uint32_t* box, int swizzle_bytes);
 int device_num_sms();
 
+// Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait()); IR_NO_PDL=1 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
 // number of kernel launches issued by this library since load (bench.py's gpu_launches counter)

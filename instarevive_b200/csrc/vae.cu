@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   const int cs = threadIdx.x % tpp, ps = threadIdx.x / tpp;
   const int p0 = chunk * chunk_px;
   const int p1 = min(P, p0 + chunk_px);
+  pdl_wait();
+  pdl_launch();
   float s_lo = 0.f, q_lo = 0.f, s_hi = 0.f, q_hi = 0.f;
   const bf16* xb = x + (long)n * P * C + cs * 8;
   auto accum = [&](const uint4& u) {
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
                                                           int nchunks, double inv_count, float eps) {
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int g = warp * 4 + k;
@@ -159,6 +163,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const int tpp = C / 8;   // 16-byte vectors per pixel; divides the block size, so a thread keeps its channel slot
   const int cpg = C / 32;
   const int c0 = (threadIdx.x % tpp) * 8;
+  pdl_wait();
+  pdl_launch();
   const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
   const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
   const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -539,20 +545,20 @@ static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
   while (div_up_l(P, chunk_px) > 1024) chunk_px *= 2;
   const int nchunks = div_up_l(P, chunk_px);
   IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
-  gn_partial_kernel<<<dim3(nchunks, c.B), 256, 0, c.s>>>(x, c.w.partial, P, C, chunk_px, nchunks);
-  IR_CUDA_CHECK(cudaGetLastError());
-  gn_finalize_kernel<<<c.B, 256, 0, c.s>>>(c.w.partial, c.w.stats, nchunks, 1.0 / ((double)P * (C / 32)), 1e-6f);
-  IR_CUDA_CHECK(cudaGetLastError());
+  IR_CUDA_CHECK(launch_pdl(gn_partial_kernel, dim3(nchunks, c.B), dim3(256), 0, c.s, x, c.w.partial, P, C, chunk_px, nchunks));
+  IR_CUDA_CHECK(launch_pdl(gn_finalize_kernel, dim3(c.B), dim3(256), 0, c.s, (const float*)c.w.partial, c.w.stats, nchunks,
+                           1.0 / ((double)P * (C / 32)), 1e-6f));
   const long total_vec = (long)c.B * P * C / 8;
   int grid = div_up_l(total_vec, 256);
   if (grid > 148 * 16) grid = 148 * 16;
   const float* gamma = vp<float>(c.v, name + ".weight");
   const float* beta = vp<float>(c.v, name + ".bias");
   if (silu_act)
-    gn_apply_kernel<true><<<grid, 256, 0, c.s>>>(x, y, c.w.stats, gamma, beta, total_vec, P, C);
+    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<true>, dim3(grid), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
+                             total_vec, P, C));
   else
-    gn_apply_kernel<false><<<grid, 256, 0, c.s>>>(x, y, c.w.stats, gamma, beta, total_vec, P, C);
-  IR_CUDA_CHECK(cudaGetLastError());
+    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<false>, dim3(grid), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
+                             total_vec, P, C));
   count_launch(3);
   return IR_OK;
 }
