@@ -9,6 +9,7 @@
 // ldm/modules/diffusionmodules/model.py:57-61,103-129,160-179.
 #include "gemm.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -22,13 +23,17 @@ static constexpr int CONV_BH = 8;
 static constexpr int STG_LD = 36;    // staging row stride in floats (32 + 4 pad: conflict-free v4 stores)
 static constexpr int NUM_THREADS = 256;
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+  // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile; each CTA stages its own
+  // 128 rows of A and BN/2 rows of B, which halves the L2 -> shared-memory traffic of the B operand per FLOP.
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
   static constexpr int BAR_BYTES = 256;
+  static constexpr int STAGES_MAX = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
   static constexpr int SMEM_BYTES = 1024 + STAGES * (A_BYTES + B_BYTES) + STG_BYTES + BAR_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
@@ -36,7 +41,8 @@ struct GemmCfg {
 struct GemmDev {
   int M, N, K;
   int k_blocks;    // K-blocks per tile
-  int m_blocks;    // M tiles per batch entry (per image for conv)
+  int m_blocks;    // 128-row M tiles per batch entry (per image for conv)
+  int m_units;     // scheduling units per batch entry: m_blocks (CG 1) or ceil(m_blocks / 2) pairs (CG 2)
   int n_blocks;
   int batch;
   int num_tiles;
@@ -61,10 +67,10 @@ struct GemmDev {
   int qkv_T, qkv_Tp, qkv_H, qkv_hd;
 };
 
-template <int BN, int EPI, bool CONV>
+template <int BN, int EPI, bool CONV, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -86,59 +92,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CG);    // CG 2: the leader's expect_tx arrive + the peer producer's remote arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * CG);  // epilogue warps of every CTA of the pair release the accumulator
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
   pdl_wait();
   pdl_launch();
 
-  const int mb_total = p.m_blocks * p.batch;
+  const int mb_total = p.m_units * p.batch;
+  const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < p.num_tiles; tile += unit_stride) {
         const int n_blk = tile / mb_total;
         const int mb = tile - n_blk * mb_total;
-        const int b = mb / p.m_blocks;
-        const int m_blk = mb - b * p.m_blocks;
+        const int b = mb / p.m_units;
+        const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;   // may exceed m_blocks (odd tail): all OOB -> zeros
         int ty = 0, tx = 0;
         if (CONV) {
           ty = m_blk / p.tiles_x;
           tx = m_blk - ty * p.tiles_x;
         }
+        const int n_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (CG == 2) {
+            if (cta_rank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+            else
+              mbar_arrive_cluster(&full_bar[stage], 0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          }
           if (CONV) {
             const int tap = kb / p.c_blocks;
             const int cb = kb - tap * p.c_blocks;
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
-                        ty * CONV_BH + dy, b);
+            if (CG == 2)
+              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
+                              ty * CONV_BH + dy, b);
+            else
+              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
+                          ty * CONV_BH + dy, b);
           } else {
-            tma_load_3d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
+            if (CG == 2)
+              tma_load_3d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
+            else
+              tma_load_3d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
           }
-          tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_blk * BN, CONV ? 0 : b);
+          if (CG == 2)
+            tma_load_3d_2sm(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, CONV ? 0 : b);
+          else
+            tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, CONV ? 0 : b);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -148,12 +180,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);  // epilogue has drained this accumulator
@@ -167,10 +199,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) inside the swizzle row: +2 in the 16 B-granular address field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CG == 2)
+              umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (kb == p.k_blocks - 1) umma_commit(&tfull_bar[buf]);
+          if (CG == 2) {
+            umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
+            if (kb == p.k_blocks - 1) umma_commit_2sm(&tfull_bar[buf], 3);
+          } else {
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == p.k_blocks - 1) umma_commit(&tfull_bar[buf]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -185,11 +225,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int col4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
       const int n_blk = tile / mb_total;
       const int mb = tile - n_blk * mb_total;
-      const int b = mb / p.m_blocks;
-      const int m_blk = mb - b * p.m_blocks;
+      const int b = mb / p.m_units;
+      const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
 
@@ -226,7 +266,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (c == BN / 32 - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+            }
           }
           if (cbase >= p.N) continue;
           const int which = cbase / D1;
@@ -330,7 +372,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -386,9 +430,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's operands / signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2)
+      tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -457,62 +505,89 @@ static int num_sms() {
 
 int device_num_sms() { return num_sms(); }
 
-template <int BN, int EPI, bool CONV>
+template <int BN, int EPI, bool CONV, int CG>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<BN, EPI, CONV>;
+  using Cfg = GemmCfg<BN, CG>;
+  auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
   static bool configured = false;
   if (!configured) {
-    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int slots = num_sms() / CG;
+  const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = CG;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (CG == 2) ? 2 : 1;
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  IR_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), GemmCfg<BN>::SMEM_BYTES, stream, ta, tw, p));
+  IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
   if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch));
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;
 }
 
-template <int BN, bool CONV>
+template <int BN, bool CONV, int CG>
 static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV>(ta, tw, p, s);
-    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV>(ta, tw, p, s);
-    case EPI_F32: return launch_inst<BN, EPI_F32, CONV>(ta, tw, p, s);
+    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, p, s);
+    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, p, s);
+    case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, p, s);
     case EPI_QKV:
-      if (!CONV) return launch_inst<BN, EPI_QKV, false>(ta, tw, p, s);
+      if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, p, s);
       break;
   }
   set_last_error("gemm: unknown epilogue %d", epi);
   return IR_ERR_INVALID;
 }
 
-static int pick_bn(long m_tiles, int N, int forced) {
-  if (forced == 64 || forced == 128 || forced == 256) return forced;
-  static int env_bn = -1;
-  if (env_bn < 0) {
-    const char* e = getenv("IR_GEMM_BN");
-    env_bn = e ? atoi(e) : 0;
+struct TileCfg {
+  int cg, bn;
+};
+
+// Tile configuration: CTA-pair tiles (cta_group::2, 256 x BN) or single-CTA tiles (128 x BN). Relative time per
+// scheduling unit calibrated on B200 (narrow tiles are bound by L2 -> shared-memory operand traffic per FLOP);
+// +15 % of a unit for the exposed last epilogue; waves = units / (SMs / CG).
+static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forced) {
+  static int env_cg = -1, env_bn = 0;
+  if (env_cg < 0) {
+    const char* e = getenv("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
+    env_cg = 0;
+    if (e) sscanf(e, "%d,%d", &env_cg, &env_bn);
   }
-  if (env_bn == 64 || env_bn == 128 || env_bn == 256) return env_bn;
+  if (forced >= 1000) return TileCfg{forced / 1000, forced % 1000};   // force_bn = cg*1000 + bn
+  if (forced == 64 || forced == 128 || forced == 256) return TileCfg{1, forced};
+  if ((env_cg == 1 || env_cg == 2) && (env_bn == 64 || env_bn == 128 || env_bn == 256) && !(env_cg == 2 && env_bn == 64))
+    return TileCfg{env_cg, env_bn};
   const int sms = num_sms();
-  int best = 128;
+  const TileCfg cands[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
+  // measured time per K-block step (us, B200, L2-resident operands): the mainloop is bound by L2 -> SM operand
+  // traffic, so wide CTA-pair tiles (128 FLOP/B) win whenever the wave quantisation allows them
+  const double unit_cost[5] = {0.50, 0.50, 0.53, 0.52, 0.41};
+  TileCfg best = cands[3];
   double best_cost = 1e30;
-  const int cands[3] = {256, 128, 64};
-  // relative cost of one tile per K-block, calibrated on B200 (8192^3: BN 256 / 128 / 64 -> 1334 / 809 / 495 TFLOP/s:
-  // narrower tiles are shared-memory-bandwidth bound on the A operand); +15 % of a tile for the exposed last epilogue
-  const double tile_cost[3] = {256.0, 206.0, 168.0};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = cands[i];
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i].bn, cg = cands[i].cg;
     if (bn > 64 && N <= bn / 2) continue;  // tile mostly empty
-    const long tiles = m_tiles * ((N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const double cost = ((double)waves + 0.15) * tile_cost[i];
+    const long units = (cg == 2 ? m_pairs_total : m_blocks_total) * ((N + bn - 1) / bn);
+    const long slots = sms / cg;
+    const long waves = (units + slots - 1) / slots;
+    const double cost = ((double)waves + 0.15) * unit_cost[i];
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
-      best = bn;
+      best = cands[i];
     }
   }
   return best;
@@ -567,7 +642,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.qkv_hd = a.qkv_hd;
 
   CUtensorMap ta, tw;
-  long m_tiles;
+  long m_blocks_total;
   if (a.conv) {
     IR_REQUIRE(a.C % BK == 0, "conv: C=%d must be a multiple of %d", a.C, BK);
     IR_REQUIRE(a.K == 9 * a.C, "conv: K=%d must equal 9*C=%d", a.K, 9 * a.C);
@@ -588,7 +663,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const uint64_t strides[3] = {(uint64_t)a.C * 2, (uint64_t)a.Wd * a.C * 2, (uint64_t)a.H * a.Wd * a.C * 2};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)CONV_BW, (uint32_t)CONV_BH, 1};
     IR_TRY(make_map(&ta, a.A, 4, dims, strides, box));
-    m_tiles = (long)p.m_blocks * a.nimg;
+    m_blocks_total = (long)p.m_blocks * a.nimg;
   } else {
     IR_REQUIRE(a.lda % 8 == 0 && a.strideA % 8 == 0, "gemm: lda/strideA must be multiples of 8 elements");
     p.m_blocks = (a.M + BM - 1) / BM;
@@ -598,33 +673,37 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const uint64_t strides[2] = {(uint64_t)a.lda * 2, (uint64_t)(ab > 1 ? a.strideA : (long)a.M * a.lda) * 2};
     const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
     IR_TRY(make_map(&ta, a.A, 3, dims, strides, box));
-    m_tiles = (long)p.m_blocks * a.batch;
+    m_blocks_total = (long)p.m_blocks * a.batch;
   }
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
-  const int bn = pick_bn(m_tiles, a.N, a.force_bn);
+  const long m_pairs = (p.m_blocks + 1) / 2;
+  const TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.force_bn);
+  const int bn = tc.bn;
+  p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;
   p.n_blocks = (a.N + bn - 1) / bn;
-  p.num_tiles = (int)(m_tiles * p.n_blocks);
+  p.num_tiles = (int)((long)p.m_units * p.batch * p.n_blocks);
   {
     const int wb = a.conv ? 1 : a.batch;
     const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)wb};
     const uint64_t strides[2] = {(uint64_t)a.ldw * 2, (uint64_t)(wb > 1 ? a.strideW : (long)a.N * a.ldw) * 2};
-    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)bn, 1};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)(bn / tc.cg), 1};
     IR_TRY(make_map(&tw, a.W, 3, dims, strides, box));
   }
 
+#define IR_DISPATCH(CONVV)                                                              \
+  if (tc.cg == 2) {                                                                     \
+    if (bn == 256) return launch_epi<256, CONVV, 2>(a.epi, ta, tw, p, stream);          \
+    return launch_epi<128, CONVV, 2>(a.epi, ta, tw, p, stream);                         \
+  }                                                                                     \
+  if (bn == 64) return launch_epi<64, CONVV, 1>(a.epi, ta, tw, p, stream);              \
+  if (bn == 128) return launch_epi<128, CONVV, 1>(a.epi, ta, tw, p, stream);            \
+  return launch_epi<256, CONVV, 1>(a.epi, ta, tw, p, stream);
   if (a.conv) {
-    switch (bn) {
-      case 64: return launch_epi<64, true>(a.epi, ta, tw, p, stream);
-      case 128: return launch_epi<128, true>(a.epi, ta, tw, p, stream);
-      default: return launch_epi<256, true>(a.epi, ta, tw, p, stream);
-    }
+    IR_DISPATCH(true)
   }
-  switch (bn) {
-    case 64: return launch_epi<64, false>(a.epi, ta, tw, p, stream);
-    case 128: return launch_epi<128, false>(a.epi, ta, tw, p, stream);
-    default: return launch_epi<256, false>(a.epi, ta, tw, p, stream);
-  }
+  IR_DISPATCH(false)
+#undef IR_DISPATCH
 }
 
 }  // namespace ir

@@ -53,7 +53,7 @@ struct GemmArgs {
   bf16* vt_heads = nullptr;
   int qkv_T = 0, qkv_Tp = 0, qkv_H = 0, qkv_hd = 0;
 
-  int force_bn = 0;  // 0 = heuristic; otherwise 64 / 128 / 256
+  int force_bn = 0;  // 0 = heuristic; 64 / 128 / 256 = single-CTA tile width; cg*1000 + bn forces (cta_group, width)
 };
 
 // bf16 tiled tensor map (innermost dimension first; strides in bytes for dims 1..rank-1; zero OOB fill).

@@ -211,10 +211,16 @@ def main():
     print(torch.cuda.get_device_name(0), L.ir_version().decode(), flush=True)
     which = sys.argv[1:] or ["gemm", "conv", "attn", "attn_tc", "ln", "perf"]
     if "gemm" in which:
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 256, 2128, 2256):
             gemm_case(256, 256, 128, 0, bn)
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 256, 2128, 2256):
             gemm_case(1024, 1152, 1152, 0, bn)
+        for bn in (2128, 2256):
+            gemm_case(1000, 3456, 1152, 0, bn)
+            gemm_case(1152, 1152, 4608, 2, bn)
+            gemm_case(384, 4608, 1152, 1, bn)
+            gemm_case(120, 2304, 1152, 0, bn, batch=5, shared_a=True)
+            gemm_case(640, 512, 512, 2, bn, batch=3)
         gemm_case(1000, 3456, 1152, 0, 0)
         gemm_case(1024, 4608, 1152, 1, 0)
         gemm_case(1024, 1152, 4608, 2, 0)
@@ -222,8 +228,11 @@ def main():
         gemm_case(512, 512, 512, 2, 128, batch=3)
         gemm_case(77, 1152, 4096, 1, 0)
     if "conv" in which:
-        for bn in (64, 128, 256):
+        for bn in (64, 128, 256, 2128, 2256):
             conv_case(1, 64, 64, 128, 256, bn)
+        conv_case(2, 24, 40, 64, 128, 2128)
+        conv_case(1, 40, 72, 128, 128, 2128)
+        conv_case(1, 64, 64, 512, 512, 2256, f32=True)
         conv_case(2, 24, 40, 64, 128, 0)
         conv_case(1, 64, 64, 512, 512, 0, f32=True)
     if "attn" in which:
@@ -243,11 +252,11 @@ def main():
     if "perf" in which:
         for (M, N, K) in [(1024, 1152, 1152), (1024, 3456, 1152), (1024, 4608, 1152), (1024, 1152, 4608),
                           (4096, 1152, 1152), (4096, 4608, 1152), (4096, 1152, 4608), (8192, 8192, 8192)]:
-            for bn in (64, 128, 256):
+            for bn in (64, 128, 256, 2128, 2256):
                 gemm_perf(M, N, K, bn)
-        for (H, C, Co) in [(64, 512, 512), (128, 512, 512), (256, 256, 256), (512, 128, 128)]:
-            for bn in (128, 256):
-                if bn <= Co:
+        for (H, C, Co) in [(64, 512, 512), (128, 512, 512), (256, 256, 256), (512, 128, 128), (1024, 128, 128)]:
+            for bn in (128, 256, 2128, 2256):
+                if bn % 1000 <= Co:
                     conv_perf(1, H, H, C, Co, bn)
     print("ALL OK" if ok_all else "SOME FAILED", flush=True)
     return 0 if ok_all else 1
