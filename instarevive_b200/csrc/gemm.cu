@@ -23,13 +23,18 @@ static constexpr int CONV_BH = 8;
 static constexpr int STG_LD = 36;    // staging row stride in floats (32 + 4 pad: conflict-free v4 stores)
 static constexpr int NUM_THREADS = 256;
 
-template <int BN, int CG>
+template <int BN, int CG, bool CONV>
 struct GemmCfg {
   // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile; each CTA stages its own
   // 128 rows of A and BN/2 rows of B, which halves the L2 -> shared-memory traffic of the B operand per FLOP.
-  static constexpr int A_BYTES = BM * BK * 2;
+  // CONV: one pipeline stage = (channel chunk, kx): a (16 x 10)-pixel halo box of the activation (160 rows of 128 B)
+  // serves the three ky taps through descriptor row offsets (+16 rows = +2048 B each, swizzle-phase preserving), and
+  // three weight tiles (one per ky). The activation is fetched 3x per channel chunk instead of 9x.
+  static constexpr int A_ROWS = CONV ? CONV_BW * (CONV_BH + 2) : BM;
+  static constexpr int A_BYTES = A_ROWS * BK * 2;
   static constexpr int B_ROWS = BN / CG;
-  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int B_TAP_BYTES = B_ROWS * BK * 2;
+  static constexpr int B_BYTES = (CONV ? 3 : 1) * B_TAP_BYTES;
   static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_MAX = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
@@ -70,8 +75,9 @@ struct GemmDev {
 template <int BN, int EPI, bool CONV, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, CONV>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(STAGES >= 2, "tile configuration does not fit a double-buffered pipeline");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -152,25 +158,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           }
           if (CONV) {
-            const int tap = kb / p.c_blocks;
-            const int cb = kb - tap * p.c_blocks;
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            // stage kb = (channel chunk cb, kx): one halo box + the three ky weight tiles
+            const int cb = kb / 3;
+            const int kx = kb - cb * 3;
             if (CG == 2)
-              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
-                              ty * CONV_BH + dy, b);
+              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx - 1,
+                              ty * CONV_BH - 1, b);
             else
-              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + dx,
-                          ty * CONV_BH + dy, b);
+              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx - 1,
+                          ty * CONV_BH - 1, b);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int kcol = ((ky * 3 + kx) * p.c_blocks + cb) * BK;
+              if (CG == 2)
+                tma_load_3d_2sm(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
+              else
+                tma_load_3d(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
+            }
           } else {
-            if (CG == 2)
+            if (CG == 2) {
               tma_load_3d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
-            else
+              tma_load_3d_2sm(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, b);
+            } else {
               tma_load_3d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM, p.a_shared ? 0 : b);
+              tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, b);
+            }
           }
-          if (CG == 2)
-            tma_load_3d_2sm(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, CONV ? 0 : b);
-          else
-            tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, CONV ? 0 : b);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -194,15 +207,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_smem_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES));
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES));
+          constexpr int TAPS = CONV ? 3 : 1;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 B (16 bf16) inside the swizzle row: +2 in the 16 B-granular address field
-            if (CG == 2)
-              umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            else
-              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int ky = 0; ky < TAPS; ++ky) {
+            // conv: tap ky reads rows [16*ky, 16*ky + 128) of the halo box (+2048 B keeps the 1024 B swizzle phase)
+            const uint64_t da = make_smem_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES + ky * (CONV_BW * BK * 2)));
+            const uint64_t db = make_smem_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 32 B (16 bf16) inside the swizzle row: +2 in the 16 B-granular address field
+              if (CG == 2)
+                umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | ky | k) != 0);
+              else
+                umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | ky | k) != 0);
+            }
           }
           if (CG == 2) {
             umma_commit_2sm(&empty_bar[stage], 3);  // frees the smem slot in both CTAs
@@ -507,7 +525,7 @@ int device_num_sms() { return num_sms(); }
 
 template <int BN, int EPI, bool CONV, int CG>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, CONV>;
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
   static bool configured = false;
   if (!configured) {
@@ -560,7 +578,7 @@ struct TileCfg {
 // Tile configuration: CTA-pair tiles (cta_group::2, 256 x BN) or single-CTA tiles (128 x BN). Relative time per
 // scheduling unit calibrated on B200 (narrow tiles are bound by L2 -> shared-memory operand traffic per FLOP);
 // +15 % of a unit for the exposed last epilogue; waves = units / (SMs / CG).
-static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forced) {
+static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forced, bool conv) {
   static int env_cg = -1, env_bn = 0;
   if (env_cg < 0) {
     const char* e = getenv("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
@@ -581,6 +599,7 @@ static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forc
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i].bn, cg = cands[i].cg;
     if (bn > 64 && N <= bn / 2) continue;  // tile mostly empty
+    if (conv && cg == 1 && bn == 256) continue;  // halo-box stages do not fit twice in shared memory
     const long units = (cg == 2 ? m_pairs_total : m_blocks_total) * ((N + bn - 1) / bn);
     const long slots = sms / cg;
     const long waves = (units + slots - 1) / slots;
@@ -655,13 +674,13 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.m_blocks = p.tiles_x * tiles_y;
     p.batch = a.nimg;  // one "batch" entry per image
     p.c_blocks = a.C / BK;
-    p.k_blocks = 9 * p.c_blocks;
+    p.k_blocks = 3 * p.c_blocks;   // pipeline steps: (channel chunk, kx), three ky taps each
     // the conv epilogue indexes the output by pixel; batch strides are folded into the pixel index
     p.stride_ob = 0;
     p.stride_of = 0;
     const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.Wd, (uint64_t)a.H, (uint64_t)a.nimg};
     const uint64_t strides[3] = {(uint64_t)a.C * 2, (uint64_t)a.Wd * a.C * 2, (uint64_t)a.H * a.Wd * a.C * 2};
-    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)CONV_BW, (uint32_t)CONV_BH, 1};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)CONV_BW, (uint32_t)(CONV_BH + 2), 1};   // halo box: ky = 0..2
     IR_TRY(make_map(&ta, a.A, 4, dims, strides, box));
     m_blocks_total = (long)p.m_blocks * a.nimg;
   } else {
@@ -678,7 +697,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
   const long m_pairs = (p.m_blocks + 1) / 2;
-  const TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.force_bn);
+  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.force_bn, a.conv != 0);
+  if (a.conv && tc.cg == 1 && tc.bn == 256) tc.bn = 128;
   const int bn = tc.bn;
   p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;
   p.n_blocks = (a.N + bn - 1) / bn;
@@ -691,19 +711,21 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     IR_TRY(make_map(&tw, a.W, 3, dims, strides, box));
   }
 
-#define IR_DISPATCH(CONVV)                                                              \
-  if (tc.cg == 2) {                                                                     \
-    if (bn == 256) return launch_epi<256, CONVV, 2>(a.epi, ta, tw, p, stream);          \
-    return launch_epi<128, CONVV, 2>(a.epi, ta, tw, p, stream);                         \
-  }                                                                                     \
-  if (bn == 64) return launch_epi<64, CONVV, 1>(a.epi, ta, tw, p, stream);              \
-  if (bn == 128) return launch_epi<128, CONVV, 1>(a.epi, ta, tw, p, stream);            \
-  return launch_epi<256, CONVV, 1>(a.epi, ta, tw, p, stream);
   if (a.conv) {
-    IR_DISPATCH(true)
+    if (tc.cg == 2) {
+      if (bn == 256) return launch_epi<256, true, 2>(a.epi, ta, tw, p, stream);
+      return launch_epi<128, true, 2>(a.epi, ta, tw, p, stream);
+    }
+    if (bn == 64) return launch_epi<64, true, 1>(a.epi, ta, tw, p, stream);
+    return launch_epi<128, true, 1>(a.epi, ta, tw, p, stream);
   }
-  IR_DISPATCH(false)
-#undef IR_DISPATCH
+  if (tc.cg == 2) {
+    if (bn == 256) return launch_epi<256, false, 2>(a.epi, ta, tw, p, stream);
+    return launch_epi<128, false, 2>(a.epi, ta, tw, p, stream);
+  }
+  if (bn == 64) return launch_epi<64, false, 1>(a.epi, ta, tw, p, stream);
+  if (bn == 128) return launch_epi<128, false, 1>(a.epi, ta, tw, p, stream);
+  return launch_epi<256, false, 1>(a.epi, ta, tw, p, stream);
 }
 
 }  // namespace ir

@@ -87,15 +87,13 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
     q_hi += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
   };
   int p = p0 + ps;
-  for (; p + 3 * pps < p1; p += 4 * pps) {  // 4 independent 16 B loads in flight per thread
-    const uint4 u0 = *reinterpret_cast<const uint4*>(xb + (long)p * C);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(xb + (long)(p + pps) * C);
-    const uint4 u2 = *reinterpret_cast<const uint4*>(xb + (long)(p + 2 * pps) * C);
-    const uint4 u3 = *reinterpret_cast<const uint4*>(xb + (long)(p + 3 * pps) * C);
-    accum(u0);
-    accum(u1);
-    accum(u2);
-    accum(u3);
+  constexpr int U = 8;  // independent 16 B loads in flight per thread
+  for (; p + (U - 1) * pps < p1; p += U * pps) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (long)(p + k * pps) * C);
+#pragma unroll
+    for (int k = 0; k < U; ++k) accum(u[k]);
   }
   for (; p < p1; p += pps) accum(*reinterpret_cast<const uint4*>(xb + (long)p * C));
   sm[threadIdx.x][0] = s_lo;
@@ -157,7 +155,7 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
 
 // Stage 3: y = act((x - mean) * rstd * gamma + beta) -> bf16; act = SiLU (x * sigmoid(x), model.py:43-45) or none.
 template <bool SILU>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, long total_vec, int P, int C) {
   const int tpp = C / 8;   // 16-byte vectors per pixel; divides the block size, so a thread keeps its channel slot
@@ -175,28 +173,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     const int n = (int)((i / tpp) / P);
     const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_lo) * 2);
     const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_hi) * 2);
-    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float2 st = k < 4 ? st_lo : st_hi;
-      float t = (v[k] - st.x) * st.y * gm[k] + bt[k];
-      if (SILU) t = silu_fast(t);
-      v[k] = t;
+    for (int k = 0; k < 4; ++k) {
+      const float2 st = k < 2 ? st_lo : st_hi;
+      const float2 a = unpack_bf16x2(w[k]);
+      float t0 = (a.x - st.x) * st.y * gm[2 * k] + bt[2 * k];
+      float t1 = (a.y - st.x) * st.y * gm[2 * k + 1] + bt[2 * k + 1];
+      if (SILU) {
+        t0 = silu_fast(t0);
+        t1 = silu_fast(t1);
+      }
+      o[k] = pack_bf16x2(t0, t1);
     }
-    *reinterpret_cast<uint4*>(y + i * 8) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   };
+  // 8 independent 16 B loads in flight per thread (HBM latency x bandwidth needs ~64 KB in flight per SM)
+  constexpr int U = 8;
   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < total_vec; i += 4 * stride) {
-    const uint4 u0 = *reinterpret_cast<const uint4*>(x + i * 8);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(x + (i + stride) * 8);
-    const uint4 u2 = *reinterpret_cast<const uint4*>(x + (i + 2 * stride) * 8);
-    const uint4 u3 = *reinterpret_cast<const uint4*>(x + (i + 3 * stride) * 8);
-    one(i, u0);
-    one(i + stride, u1);
-    one(i + 2 * stride, u2);
-    one(i + 3 * stride, u3);
+  for (; i + (U - 1) * stride < total_vec; i += U * stride) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (i + k * stride) * 8);
+#pragma unroll
+    for (int k = 0; k < U; ++k) one(i + k * stride, u[k]);
   }
   for (; i < total_vec; i += stride) one(i, *reinterpret_cast<const uint4*>(x + i * 8));
 }
@@ -205,17 +206,32 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 // F.interpolate(scale_factor=2.0, mode="nearest") on NHWC bf16 (Upsample.forward, model.py:63-67).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long total_vec,
                                                          int H, int W, int C) {
+  // total_vec counts INPUT vectors: every 16 B input vector is read once and written to its 2x2 output pixels
   const int tpp = C / 8;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total_vec; i += (long)gridDim.x * blockDim.x) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  auto emit = [&](long i, const uint4& u) {
     const int cv = (int)(i % tpp);
     long pix = i / tpp;
-    const int xo = (int)(pix % (2 * W));
-    pix /= 2 * W;
-    const int yo = (int)(pix % (2 * H));
-    const long n = pix / (2 * H);
-    const uint4 u = *reinterpret_cast<const uint4*>(x + (((n * H + (yo >> 1)) * W + (xo >> 1)) * (long)C) + cv * 8);
-    *reinterpret_cast<uint4*>(y + i * 8) = u;
+    const int xi = (int)(pix % W);
+    pix /= W;
+    const int yi = (int)(pix % H);
+    const long n = pix / H;
+    bf16* o = y + (((n * 2 * H + 2 * yi) * 2 * W + 2 * xi) * (long)C) + cv * 8;
+    *reinterpret_cast<uint4*>(o) = u;
+    *reinterpret_cast<uint4*>(o + C) = u;
+    *reinterpret_cast<uint4*>(o + 2L * W * C) = u;
+    *reinterpret_cast<uint4*>(o + 2L * W * C + C) = u;
+  };
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < total_vec; i += U * stride) {
+    uint4 u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (i + k * stride) * 8);
+#pragma unroll
+    for (int k = 0; k < U; ++k) emit(i + k * stride, u[k]);
   }
+  for (; i < total_vec; i += stride) emit(i, *reinterpret_cast<const uint4*>(x + i * 8));
 }
 
 // ------------------------------------------------------------------------------------------------ attention helpers
@@ -708,7 +724,7 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
     }
     if (lvl != 0) {
       bf16* up = c.w.buf[(cur + 1) & 3];
-      const long total_vec = (long)B * (2 * H) * (2 * W) * C / 8;
+      const long total_vec = (long)B * H * W * C / 8;   // input vectors
       int grid = div_up_l(total_vec, 256);
       if (grid > 148 * 16) grid = 148 * 16;
       upsample2x_kernel<<<grid, 256, 0, s>>>(c.w.buf[cur], up, total_vec, H, W, C);
