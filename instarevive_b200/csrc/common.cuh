@@ -96,6 +96,22 @@ IR_DEVINL float silu_fast(float x) {
   return x * (0.5f * t + 0.5f);
 }
 
+// ---------------------------------------------------------------- explicit shared-memory vector access
+// (keeps ptxas from falling back to generic LD/ST when pointer provenance is lost through lambdas / casts)
+IR_DEVINL void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+IR_DEVINL float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+IR_DEVINL float lds_f1(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor is still
 // draining; it must execute pdl_wait() before its first global-memory access that depends on (or could overwrite data

@@ -58,6 +58,7 @@ struct GemmDev {
   const float* bias;
   long stride_bias;
   int a_shared;  // all batch entries read A at batch coordinate 0
+  int dbg_nomma; // experiment: skip the MMAs (times the TMA/L2 path alone; results are garbage)
   bf16* out_bf16;
   const bf16* resid_bf16;
   long ldo_b, stride_ob;
@@ -208,6 +209,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           constexpr int TAPS = CONV ? 3 : 1;
+          if (CG == 1 && p.dbg_nomma) {
+            mbar_arrive(&empty_bar[stage]);
+            if (kb == p.k_blocks - 1) mbar_arrive(&tfull_bar[buf]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
 #pragma unroll
           for (int ky = 0; ky < TAPS; ++ky) {
             // conv: tap ky reads rows [16*ky, 16*ky + 128) of the halo box (+2048 B keeps the 1024 B swizzle phase)
@@ -240,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
     const int q = warp - 4;  // TMEM lane quarter: lanes [32q, 32q+32)
     float* stg = staging + q * (32 * STG_LD);
+    const uint32_t stg_s = smem_u32(stg);
     const int col4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
     int it = 0;
@@ -272,6 +283,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
 
+      // Residual reads are software-pipelined one 32-column chunk ahead (two chunks of loads in flight per warp): the
+      // epilogue is latency-bound on these loads, not bandwidth-bound.
+      float4 res_cur[8], res_nxt[8];
+      uint2 resb_cur[8], resb_nxt[8];
+      auto load_resid = [&](int cc, float4 (&r4)[8], uint2 (&rb)[8]) {
+        const int ccol = n_blk * BN + cc * 32 + col4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = row_off[i] >= 0 && ccol < p.N;
+          if (EPI == EPI_F32) {
+            r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && p.resid_f32)
+              r4[i] = *reinterpret_cast<const float4*>(p.resid_f32 + (long)b * p.stride_of + row_off[i] * p.ldo_f + ccol);
+          } else if (EPI == EPI_BF16) {
+            rb[i] = make_uint2(0u, 0u);
+            if (ok && p.resid_bf16)
+              rb[i] = *reinterpret_cast<const uint2*>(p.resid_bf16 + (long)b * p.stride_ob + row_off[i] * p.ldo_b + ccol);
+          }
+        }
+      };
+      if (EPI == EPI_F32 || EPI == EPI_BF16) load_resid(0, res_cur, resb_cur);
+      const bool gate_uniform = gate_row[0] == gate_row[7];
+
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         if (EPI == EPI_QKV) {
@@ -301,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) {
                 float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+                sts_f4(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, f);
               }
               __syncwarp();
               const int cl = cbase + lane - 2 * D1;
@@ -312,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int g = 0; g < 4; ++g) {
                 float e[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = stg[(g * 8 + i) * STG_LD + lane] + bv;
+                for (int i = 0; i < 8; ++i) e[i] = lds_f1(stg_s + (uint32_t)((g * 8 + i) * STG_LD + lane) * 4u) + bv;
                 *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
                                                                     pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
               }
@@ -335,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 8; ++j) {
               float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-              *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+              sts_f4(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, f);
             }
             __syncwarp();
             const int cl = cbase + col4 - which * D1;
@@ -347,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (row_off[i] < 0) continue;
               const int gm = (int)row_off[i];
               const int bb = gm / p.qkv_T, t = gm - bb * p.qkv_T;
-              float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * STG_LD + col4);
+              float4 a = lds_f4(stg_s + (uint32_t)((i * 4 + rsub) * STG_LD + col4) * 4u);
               *reinterpret_cast<uint2*>(dst + (((long)bb * p.qkv_H + head) * p.qkv_T + t) * p.qkv_hd + d) =
                   make_uint2(pack_bf16x2(a.x + bias4.x, a.y + bias4.y), pack_bf16x2(a.z + bias4.z, a.w + bias4.w));
             }
@@ -357,28 +391,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int col = n_blk * BN + c * 32 + col4;
         const bool col_ok = col < p.N;
-        // Prefetch everything the epilogue reads from global memory BEFORE the TMEM load: the output may alias the
-        // residual (in-place x += ...), so loads issued after the first store could not be hoisted by the compiler.
-        float4 res4[8];
+        // Everything the epilogue reads from global memory is issued BEFORE the TMEM load (and the residual of the NEXT
+        // chunk now): the output may alias the residual (in-place x += ...), so loads placed after the first store
+        // could not be hoisted by the compiler.
         float4 gate4[8];
-        uint2 resb[8];
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 1 < BN / 32 && (EPI == EPI_F32 || EPI == EPI_BF16)) load_resid(c + 1, res_nxt, resb_nxt);
         if (col_ok) {
           if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
+          if (EPI == EPI_F32) {
+            if (!p.gate) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = row_off[i] >= 0;
-            if (EPI == EPI_F32) {
-              res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              gate4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (ok && p.resid_f32)
-                res4[i] = *reinterpret_cast<const float4*>(p.resid_f32 + (long)b * p.stride_of + row_off[i] * p.ldo_f + col);
-              if (ok && p.gate)
+              for (int i = 0; i < 8; ++i) gate4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            } else if (gate_uniform) {
+              const float4 g = *reinterpret_cast<const float4*>(p.gate + (long)gate_row[0] * p.gate_ld + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) gate4[i] = g;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
                 gate4[i] = *reinterpret_cast<const float4*>(p.gate + (long)gate_row[i] * p.gate_ld + col);
-            } else if (EPI == EPI_BF16) {
-              resb[i] = make_uint2(0u, 0u);
-              if (ok && p.resid_bf16)
-                resb[i] = *reinterpret_cast<const uint2*>(p.resid_bf16 + (long)b * p.stride_ob + row_off[i] * p.ldo_b + col);
             }
           }
         }
@@ -398,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 8; ++j) {
           float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = f;
+          sts_f4(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u, f);
         }
         __syncwarp();
 
@@ -406,7 +438,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (row_off[i] < 0) continue;
-            float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * STG_LD + col4);
+            float4 a = lds_f4(stg_s + (uint32_t)((i * 4 + rsub) * STG_LD + col4) * 4u);
             a.x = a.x * p.alpha + bias4.x;
             a.y = a.y * p.alpha + bias4.y;
             a.z = a.z * p.alpha + bias4.z;
@@ -419,10 +451,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (EPI == EPI_F32) {
               const long o = (long)b * p.stride_of + row_off[i] * p.ldo_f + col;
-              a.x = a.x * gate4[i].x + res4[i].x;
-              a.y = a.y * gate4[i].y + res4[i].y;
-              a.z = a.z * gate4[i].z + res4[i].z;
-              a.w = a.w * gate4[i].w + res4[i].w;
+              a.x = a.x * gate4[i].x + res_cur[i].x;
+              a.y = a.y * gate4[i].y + res_cur[i].y;
+              a.z = a.z * gate4[i].z + res_cur[i].z;
+              a.w = a.w * gate4[i].w + res_cur[i].w;
               *reinterpret_cast<float4*>(p.out_f32 + o) = a;
               if (p.out_bf16) {
                 const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
@@ -431,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               const long ob = (long)b * p.stride_ob + row_off[i] * p.ldo_b + col;
               if (EPI == EPI_BF16) {
-                const float2 r0 = unpack_bf16x2(resb[i].x), r1 = unpack_bf16x2(resb[i].y);
+                const float2 r0 = unpack_bf16x2(resb_cur[i].x), r1 = unpack_bf16x2(resb_cur[i].y);
                 a.x += r0.x;
                 a.y += r0.y;
                 a.z += r1.x;
@@ -442,6 +474,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          res_cur[i] = res_nxt[i];
+          resb_cur[i] = resb_nxt[i];
+        }
       }
     }
   }
@@ -641,6 +678,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.stride_bias = a.conv ? 0 : a.stride_bias;
   p.a_shared = (!a.conv && a.batch > 1 && a.strideA == 0) ? 1 : 0;
+  {
+    static const int nomma = [] { const char* e = getenv("IR_GEMM_NOMMA"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.dbg_nomma = nomma;
+  }
   p.out_bf16 = a.out_bf16;
   p.resid_bf16 = a.resid_bf16;
   p.ldo_b = a.ldo_b;
