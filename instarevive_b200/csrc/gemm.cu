@@ -68,6 +68,9 @@ struct GemmDev {
   const float* gate;
   long gate_ld;
   int rows_per_gate;
+  // fused GroupNorm statistics
+  float* gn_partial;
+  int gn_cpg, gn_rows_per_img;
   // EPI_QKV
   bf16 *q_heads, *k_heads, *vt_heads;
   int qkv_T, qkv_Tp, qkv_H, qkv_hd;
@@ -253,6 +256,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stg_s = smem_u32(stg);
     const int col4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
+    // fused GroupNorm statistics: per-lane (sum, sum of squares) of its 4 channels per 32-column chunk over the rows of
+    // ONE tile, reduced by a fixed shuffle tree and written to the slot of (image, tile, warp). Per-tile partials do not
+    // depend on how tiles are scheduled or batched, so the statistics are bit-reproducible for any sharding.
+    float gn_s[BN / 32], gn_q[BN / 32];
+    const bool gn_on = (EPI == EPI_BF16) && p.gn_partial != nullptr;
     int it = 0;
     for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
       const int n_blk = tile / mb_total;
@@ -261,6 +269,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
+      if (gn_on) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          gn_s[c] = 0.f;
+          gn_q[c] = 0.f;
+        }
+      }
 
       // per-lane row bookkeeping for the 8 rows this lane touches after the transpose
       long row_off[8];   // row index into the output (rows of ldo elements), -1 if masked
@@ -396,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // could not be hoisted by the compiler.
         float4 gate4[8];
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float chunk_s = 0.f, chunk_q = 0.f;
         if (c + 1 < BN / 32 && (EPI == EPI_F32 || EPI == EPI_BF16)) load_resid(c + 1, res_nxt, resb_nxt);
         if (col_ok) {
           if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
@@ -470,15 +486,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 a.w += r1.y;
               }
               *reinterpret_cast<uint2*>(p.out_bf16 + ob) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              if (gn_on) {   // statistics of the fp32 values (what the reference normalises), before bf16 rounding
+                chunk_s += (a.x + a.y) + (a.z + a.w);
+                chunk_q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, chunk_q))));
+              }
             }
           }
         }
         __syncwarp();
+        if (gn_on) {
+#pragma unroll
+          for (int cc = 0; cc < BN / 32; ++cc) {   // static indexing keeps the accumulators in registers
+            if (cc == c) {
+              gn_s[cc] += chunk_s;
+              gn_q[cc] += chunk_q;
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           res_cur[i] = res_nxt[i];
           resb_cur[i] = resb_nxt[i];
         }
+      }
+      if (gn_on) {
+        // reduce over the lanes that share a group (fixed tree), park the per-warp group sums in this warp's staging
+        // area, combine the 4 epilogue warps in fixed order and write ONE partial per (image, tile, group)
+        const int tiles_per_img = CONV ? p.m_blocks : p.gn_rows_per_img / BM;
+        const int img = CONV ? b : m_blk / tiles_per_img;
+        const int tile_in_img = CONV ? m_blk : m_blk - img * tiles_per_img;
+        const int gpc = 32 / p.gn_cpg;   // groups per 32-column chunk
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          float s_ = gn_s[c], q_ = gn_q[c];
+          s_ += __shfl_xor_sync(0xffffffffu, s_, 8);
+          q_ += __shfl_xor_sync(0xffffffffu, q_, 8);
+          s_ += __shfl_xor_sync(0xffffffffu, s_, 16);
+          q_ += __shfl_xor_sync(0xffffffffu, q_, 16);
+          if (p.gn_cpg >= 8) {
+            s_ += __shfl_xor_sync(0xffffffffu, s_, 1);
+            q_ += __shfl_xor_sync(0xffffffffu, q_, 1);
+          }
+          if (p.gn_cpg >= 16) {
+            s_ += __shfl_xor_sync(0xffffffffu, s_, 2);
+            q_ += __shfl_xor_sync(0xffffffffu, q_, 2);
+          }
+          if (rsub == 0 && (col4 % p.gn_cpg) == 0) {
+            const int gi = c * gpc + col4 / p.gn_cpg;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stg_s + (uint32_t)gi * 8u), "f"(s_), "f"(q_) : "memory");
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q == 0 && m_blk < p.m_blocks) {
+          const uint32_t stg0 = smem_u32(staging);
+          for (int gi = lane; gi < (BN / 32) * gpc; gi += 32) {
+            const int gcol = n_blk * BN + gi * p.gn_cpg;
+            if (gcol < p.N) {
+              float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                float a0, a1;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0), "=f"(a1) : "r"(stg0 + (uint32_t)(w * 32 * STG_LD * 4 + gi * 8)) : "memory");
+                s_ += a0;
+                q_ += a1;
+              }
+              const long slot = (long)img * tiles_per_img + tile_in_img;
+              *reinterpret_cast<float2*>(p.gn_partial + (slot * 32 + gcol / p.gn_cpg) * 2) = make_float2(s_, q_);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging is reused by the next tile's first chunk
       }
     }
   }
@@ -559,6 +636,7 @@ static int num_sms() {
 }
 
 int device_num_sms() { return num_sms(); }
+int gemm_conv_tiles_per_image(int H, int W) { return ((W + CONV_BW - 1) / CONV_BW) * ((H + CONV_BH - 1) / CONV_BH); }
 
 template <int BN, int EPI, bool CONV, int CG>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
@@ -668,6 +746,11 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     IR_REQUIRE(a.out_bf16 && a.ldo_b % 4 == 0, "gemm: bf16 epilogue needs out_bf16 with ld %% 4 == 0");
   }
   IR_REQUIRE(!a.gate || a.gate_ld % 4 == 0, "gemm: gate_ld must be a multiple of 4");
+  if (a.gn_partial) {
+    IR_REQUIRE(a.epi == EPI_BF16 && (a.gn_cpg == 4 || a.gn_cpg == 8 || a.gn_cpg == 16) && a.N == 32 * a.gn_cpg,
+               "gemm: fused GroupNorm statistics need EPI_BF16 and N == 32 * cpg");
+    IR_REQUIRE(a.conv || (a.batch == 1 && a.gn_rows_per_img % BM == 0), "gemm: fused GroupNorm statistics need rows_per_img %% 128 == 0");
+  }
 
   GemmDev p{};
   p.M = a.M;
@@ -693,6 +776,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.gate = a.gate;
   p.gate_ld = a.gate_ld;
   p.rows_per_gate = a.rows_per_gate > 0 ? a.rows_per_gate : 1;
+  p.gn_partial = a.gn_partial;
+  p.gn_cpg = a.gn_cpg;
+  p.gn_rows_per_img = a.gn_rows_per_img > 0 ? a.gn_rows_per_img : 1;
   p.q_heads = a.q_heads;
   p.k_heads = a.k_heads;
   p.vt_heads = a.vt_heads;

@@ -47,6 +47,14 @@ struct GemmArgs {
   long gate_ld = 0;
   int rows_per_gate = 1;
 
+  // Optional fused GroupNorm statistics (EPI_BF16 only): per (image, group) sum / sum of squares of the STORED bf16
+  // output, written as per-(tile, warp) partials gn_partial[img][tile][32][2] (the 4 epilogue warps are combined in fixed order; every entry is written exactly
+  // once: no zeroing; tile = 128-row tile index inside the image). Requires N == 32 * gn_cpg; plain GEMM:
+  // gn_rows_per_img % 128 == 0.
+  float* gn_partial = nullptr;
+  int gn_cpg = 0;
+  int gn_rows_per_img = 0;
+
   // EPI_QKV only: N = 3*H*hd, rows are (b, t) with T tokens per sample
   bf16* q_heads = nullptr;
   bf16* k_heads = nullptr;
@@ -61,6 +69,7 @@ struct GemmArgs {
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes);
 int device_num_sms();
+int gemm_conv_tiles_per_image(int H, int W);  // 128-pixel tiles per image of the implicit-GEMM conv
 
 // Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait()); IR_NO_PDL=1 disables it.
 bool pdl_enabled();

@@ -153,6 +153,39 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
   }
 }
 
+// Finalize for the statistics fused into the GEMM / conv epilogue: partial[img][slot][32][2], slot = 128-row tile.
+// One block per (image, group); threads stride over the slots in double precision, fixed smem tree (deterministic).
+__global__ void __launch_bounds__(256) gn_finalize_fused_kernel(const float* __restrict__ partial, float* __restrict__ stats,
+                                                                int nslots, double inv_count, float eps) {
+  __shared__ double red[2][256];
+  const int n = blockIdx.x, g = blockIdx.y;
+  pdl_wait();
+  pdl_launch();
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < nslots; i += 256) {
+    const float2 pp = *reinterpret_cast<const float2*>(partial + (((long)n * nslots + i) * 32 + g) * 2);
+    s += (double)pp.x;
+    q += (double)pp.y;
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = red[0][0] * inv_count;
+    double var = red[1][0] * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((long)n * 32 + g) * 2] = (float)mean;
+    stats[((long)n * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // Stage 3: y = act((x - mean) * rstd * gamma + beta) -> bf16; act = SiLU (x * sigmoid(x), model.py:43-45) or none.
 template <bool SILU>
 __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
@@ -491,6 +524,7 @@ struct VaeWs {
   bf16* buf[4];
   bf16 *qkv, *vt, *pm;
   float *scores, *partial, *stats;
+  long partial_elems;
 };
 
 static const int GN_MAX_CHUNKS = 2048;
@@ -526,7 +560,9 @@ static size_t vae_carve(const Vae* v, VaeWs& w, void* base, int B, int h, int wd
   w.vt = reinterpret_cast<bf16*>(take((size_t)P * C * sizeof(bf16)));
   w.pm = reinterpret_cast<bf16*>(take((size_t)P * P * sizeof(bf16)));
   w.scores = reinterpret_cast<float*>(take((size_t)P * P * sizeof(float)));
-  w.partial = reinterpret_cast<float*>(take((size_t)B * GN_MAX_CHUNKS * 32 * 2 * sizeof(float)));
+  // GroupNorm partials: standalone pass (<= GN_MAX_CHUNKS chunks) or fused (4 warps x 128-pixel tiles at full resolution)
+  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(8 * h, 8 * wd)) * 64;
+  w.partial = reinterpret_cast<float*>(take((size_t)w.partial_elems * sizeof(float)));
   w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
   return (off + 255) & ~size_t(255);
 }
@@ -541,6 +577,7 @@ struct VCtx {
   VaeWs w;
   int B;
   cudaStream_t s;
+  bool stats_ready = false;   // c.w.stats already holds (mean, rstd) of the tensor the next group_norm will see
 };
 
 template <typename T>
@@ -555,15 +592,20 @@ static const T* vp(const Vae* v, const std::string& name) {
 // y = act(GroupNorm(x)); x, y: (B, P, C) NHWC bf16
 static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, int P, int C, bool silu_act) {
   IR_REQUIRE(C % 32 == 0 && (C / 32 == 4 || C / 32 == 8 || C / 32 == 16), "group_norm: C=%d unsupported", C);
-  // The chunking must depend on the image size only (never on the batch): the fp32 partial sums are then grouped
-  // identically however tiles are batched or sharded across GPUs, which keeps tiled restoration bit-reproducible.
-  int chunk_px = 256;
-  while (div_up_l(P, chunk_px) > 1024) chunk_px *= 2;
-  const int nchunks = div_up_l(P, chunk_px);
-  IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
-  IR_CUDA_CHECK(launch_pdl(gn_partial_kernel, dim3(nchunks, c.B), dim3(256), 0, c.s, x, c.w.partial, P, C, chunk_px, nchunks));
-  IR_CUDA_CHECK(launch_pdl(gn_finalize_kernel, dim3(c.B), dim3(256), 0, c.s, (const float*)c.w.partial, c.w.stats, nchunks,
-                           1.0 / ((double)P * (C / 32)), 1e-6f));
+  if (c.stats_ready) {
+    c.stats_ready = false;   // statistics were produced by the epilogue of the kernel that wrote x
+  } else {
+    // The chunking must depend on the image size only (never on the batch): the fp32 partial sums are then grouped
+    // identically however tiles are batched or sharded across GPUs, which keeps tiled restoration bit-reproducible.
+    int chunk_px = 256;
+    while (div_up_l(P, chunk_px) > 1024) chunk_px *= 2;
+    const int nchunks = div_up_l(P, chunk_px);
+    IR_REQUIRE(nchunks <= GN_MAX_CHUNKS, "group_norm: too many chunks");
+    IR_CUDA_CHECK(launch_pdl(gn_partial_kernel, dim3(nchunks, c.B), dim3(256), 0, c.s, x, c.w.partial, P, C, chunk_px, nchunks));
+    IR_CUDA_CHECK(launch_pdl(gn_finalize_kernel, dim3(c.B), dim3(256), 0, c.s, (const float*)c.w.partial, c.w.stats, nchunks,
+                             1.0 / ((double)P * (C / 32)), 1e-6f));
+    count_launch(2);
+  }
   const long total_vec = (long)c.B * P * C / 8;
   int grid = div_up_l(total_vec, 256);
   if (grid > 148 * 16) grid = 148 * 16;
@@ -579,8 +621,20 @@ static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
   return IR_OK;
 }
 
+// After a GEMM / conv launched with fused statistics: reduce the per-(CTA, warp) partials to (mean, rstd).
+static int finish_fused_stats(VCtx& c, int P, int C, int nslots) {
+  IR_CUDA_CHECK(launch_pdl(gn_finalize_fused_kernel, dim3(c.B, 32), dim3(256), 0, c.s, (const float*)c.w.partial, c.w.stats,
+                           nslots, 1.0 / ((double)P * (C / 32)), 1e-6f));
+  count_launch();
+  c.stats_ready = true;
+  return IR_OK;
+}
+
+static bool fused_stats_ok(int C) { return C % 32 == 0 && (C / 32 == 4 || C / 32 == 8 || C / 32 == 16); }
+
+// want_stats: the output feeds a GroupNorm next, so its statistics are accumulated in the epilogue
 static int conv3x3(VCtx& c, const std::string& name, const bf16* x, bf16* y, const bf16* resid, int H, int W, int Cin,
-                   int Cout) {
+                   int Cout, bool want_stats) {
   GemmArgs g;
   g.A = x;
   g.W = vp<bf16>(c.v, name + ".weight");
@@ -598,11 +652,19 @@ static int conv3x3(VCtx& c, const std::string& name, const bf16* x, bf16* y, con
   g.out_bf16 = y;
   g.resid_bf16 = resid;
   g.ldo_b = Cout;
-  return gemm_launch(g, c.s);
+  const int nslots = gemm_conv_tiles_per_image(H, W);
+  const bool fuse = want_stats && fused_stats_ok(Cout) && (long)c.B * nslots * 64 <= c.w.partial_elems;
+  if (fuse) {
+    g.gn_partial = c.w.partial;
+    g.gn_cpg = Cout / 32;
+  }
+  IR_TRY(gemm_launch(g, c.s));
+  if (fuse) IR_TRY(finish_fused_stats(c, H * W, Cout, nslots));
+  return IR_OK;
 }
 
 static int conv1x1(VCtx& c, const bf16* wgt, const float* bias, const bf16* x, bf16* y, const bf16* resid, long M,
-                   int Cin, int Cout) {
+                   int Cin, int Cout, int stats_P = 0) {
   GemmArgs g;
   g.A = x;
   g.lda = Cin;
@@ -616,18 +678,27 @@ static int conv1x1(VCtx& c, const bf16* wgt, const float* bias, const bf16* x, b
   g.out_bf16 = y;
   g.resid_bf16 = resid;
   g.ldo_b = Cout;
-  return gemm_launch(g, c.s);
+  const int nslots = stats_P / 128;
+  const bool fuse = stats_P > 0 && stats_P % 128 == 0 && fused_stats_ok(Cout) && (long)c.B * nslots * 64 <= c.w.partial_elems;
+  if (fuse) {
+    g.gn_partial = c.w.partial;
+    g.gn_cpg = Cout / 32;
+    g.gn_rows_per_img = stats_P;
+  }
+  IR_TRY(gemm_launch(g, c.s));
+  if (fuse) IR_TRY(finish_fused_stats(c, stats_P, Cout, nslots));
+  return IR_OK;
 }
 
 // ResnetBlock.forward (model.py:131-151); h lives in buf[cur]; returns the index of the buffer holding the result
-static int res_block(VCtx& c, const std::string& name, int& cur, int H, int W, int Cin, int Cout) {
+static int res_block(VCtx& c, const std::string& name, int& cur, int H, int W, int Cin, int Cout, bool out_feeds_norm) {
   const int P = H * W;
   bf16* x = c.w.buf[cur];
   bf16* t1 = c.w.buf[(cur + 1) & 3];
   bf16* t2 = c.w.buf[(cur + 2) & 3];
   bf16* t3 = c.w.buf[(cur + 3) & 3];
   IR_TRY(group_norm(c, name + ".norm1", x, t1, P, Cin, true));
-  IR_TRY(conv3x3(c, name + ".conv1", t1, t2, nullptr, H, W, Cin, Cout));
+  IR_TRY(conv3x3(c, name + ".conv1", t1, t2, nullptr, H, W, Cin, Cout, true));
   IR_TRY(group_norm(c, name + ".norm2", t2, t1, P, Cout, true));
   const bf16* skip = x;
   if (Cin != Cout) {
@@ -635,7 +706,7 @@ static int res_block(VCtx& c, const std::string& name, int& cur, int H, int W, i
                    nullptr, (long)c.B * P, Cin, Cout));
     skip = t2;
   }
-  IR_TRY(conv3x3(c, name + ".conv2", t1, t3, skip, H, W, Cout, Cout));
+  IR_TRY(conv3x3(c, name + ".conv2", t1, t3, skip, H, W, Cout, Cout, out_feeds_norm));
   cur = (cur + 3) & 3;
   return IR_OK;
 }
@@ -678,7 +749,7 @@ static int attn_block(VCtx& c, const std::string& name, int& cur, int H, int W, 
     count_launch(2);
   }
   IR_TRY(conv1x1(c, vp<bf16>(c.v, name + ".proj_out.weight"), vp<float>(c.v, name + ".proj_out.bias"), ao, y, x,
-                 (long)c.B * P, C, C));
+                 (long)c.B * P, C, C, P));   // feeds mid.block_2.norm1
   cur = (cur + 3) & 3;
   return IR_OK;
 }
@@ -713,13 +784,15 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
     IR_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
-  IR_TRY(res_block(c, d + ".mid.block_1", cur, H, W, C, C));
+  IR_TRY(res_block(c, d + ".mid.block_1", cur, H, W, C, C, true));
   IR_TRY(attn_block(c, d + ".mid.attn_1", cur, H, W, C));
-  IR_TRY(res_block(c, d + ".mid.block_2", cur, H, W, C, C));
+  IR_TRY(res_block(c, d + ".mid.block_2", cur, H, W, C, C, true));
   for (int lvl = 3; lvl >= 0; --lvl) {
     const int Cout = cfg.ch * cfg.ch_mult[lvl];
     for (int b = 0; b < cfg.num_res_blocks + 1; ++b) {
-      IR_TRY(res_block(c, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), cur, H, W, C, Cout));
+      // the last block of a level is followed by the (norm-free) upsample, except at level 0 (norm_out)
+      const bool feeds_norm = (b < cfg.num_res_blocks) || lvl == 0;
+      IR_TRY(res_block(c, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), cur, H, W, C, Cout, feeds_norm));
       C = Cout;
     }
     if (lvl != 0) {
@@ -733,7 +806,7 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
       H *= 2;
       W *= 2;
       IR_TRY(conv3x3(c, d + ".up." + std::to_string(lvl) + ".upsample.conv", up, c.w.buf[(cur + 2) & 3], nullptr, H, W,
-                     C, C));
+                     C, C, true));
       cur = (cur + 2) & 3;
     }
   }
