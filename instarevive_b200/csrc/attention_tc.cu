@@ -21,7 +21,7 @@ constexpr int HD = 72;
 constexpr int BQ = 128;          // rows per query tile (UMMA M)
 constexpr int BKV = 128;         // keys per tile (UMMA N of S, K of P*V)
 constexpr int NV = 80;           // head dim padded to a multiple of 16 (UMMA N of P*V)
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int Q64_BYTES = BQ * 64 * 2;    // 16384
 constexpr int Q16_BYTES = BQ * 16 * 2;    // 4096
 constexpr int QTILE_BYTES = Q64_BYTES + Q16_BYTES;
@@ -66,7 +66,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   uint64_t* s_full = bars + 1 + 2 * STAGES;   // [2]
   uint64_t* p_full = s_full + 2;              // [2]
   uint64_t* o_full = p_full + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;              // [2] softmax has copied S into registers: S buffer may be overwritten
+  uint64_t* pv_done = s_free + 2;             // [2] P*V of the previous tile finished: P smem / O TMEM may be touched
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ;
@@ -90,6 +92,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], BQ);
       mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], BQ);
+      mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -160,32 +164,40 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == STAGES) {
-          nstage = 0;
-          nphase ^= 1;
-        }
+      // Event-driven issue: per query tile, S(t) may go as soon as the softmax warps have copied S(t-1) out of TMEM
+      // (s_free) and K(t) has landed; P*V(t) as soon as P(t) is in shared memory (p_full). Polling both query tiles
+      // keeps the tensor core fed whichever softmax group finishes first.
+      int s_next[2] = {1, 1}, pv_next[2] = {0, 0};
+      int kv_seen = 0;       // tiles [0, kv_seen] have landed
+      int kv_released = 0;   // tiles [0, kv_released) have been handed back to the producer
+      while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
+#pragma unroll
         for (int qt = 0; qt < 2; ++qt) {
-          mbar_wait(&p_full[qt], (uint32_t)(j & 1));  // P_qt(j) is in smem and the O rescale (if any) is done
-          tc_fence_after();
-          issue_pv(qt, stage, j > 0);
-          if (j + 1 < n_tiles) {
-            if (qt == 0) {
-              mbar_wait(&kv_full[nstage], nphase);
+          const int ts = s_next[qt];
+          if (ts < n_tiles) {
+            if (ts > kv_seen && mbar_try_wait(&kv_full[ts % STAGES], (uint32_t)((ts / STAGES) & 1))) kv_seen = ts;
+            if (ts <= kv_seen && mbar_try_wait(&s_free[qt], (uint32_t)((ts - 1) & 1))) {
               tc_fence_after();
+              issue_s(qt, ts % STAGES);
+              s_next[qt] = ts + 1;
             }
-            issue_s(qt, nstage);  // its commit also covers P*V(qt, j): frees P_qt and publishes O_qt(j)
-          } else {
-            umma_commit(&o_full[qt]);
+          }
+          const int tp = pv_next[qt];
+          if (tp < n_tiles && mbar_try_wait(&p_full[qt], (uint32_t)(tp & 1))) {
+            tc_fence_after();
+            issue_pv(qt, tp % STAGES, tp > 0);
+            if (tp + 1 < n_tiles)
+              umma_commit(&pv_done[qt]);   // softmax(qt, tp+1) may overwrite P_qt / rescale O_qt once this fires
+            else
+              umma_commit(&o_full[qt]);
+            pv_next[qt] = tp + 1;
+            const int done = pv_next[0] < pv_next[1] ? pv_next[0] : pv_next[1];
+            while (kv_released < done) {
+              umma_commit(&kv_empty[kv_released % STAGES]);   // both P*V(kv_released) issued: stage can be refilled
+              ++kv_released;
+            }
           }
         }
-        umma_commit(&kv_empty[stage]);
-        stage = nstage;
-        phase = nphase;
       }
     }
   } else {
@@ -205,6 +217,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[qt]);   // S lives in registers now: the tensor core may start S(qt, j+1)
       const int kbase = j * BKV;
       float mx = -INFINITY;
       if (kbase + BKV <= p.T) {
@@ -222,6 +236,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
           }
       }
       const float m_new = fmaxf(m_used, mx * p.scale_log2e);
+      if (j > 0) {
+        // P*V(qt, j-1) must have finished reading P_qt and accumulating into O_qt before either is touched again
+        mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
       // lazy rescale: keep the stale max unless it grew by more than 8 (p stays below 2^8, exact in fp32 / fine in bf16)
       const bool grow = (m_new - m_used) > 8.0f;   // also true on the first tile (m_used = -inf)
       if (__any_sync(0xffffffffu, grow)) {

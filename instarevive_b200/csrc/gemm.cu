@@ -708,7 +708,7 @@ static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forc
   const TileCfg cands[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
   // measured time per K-block step (us, B200, L2-resident operands): the mainloop is bound by L2 -> SM operand
   // traffic, so wide CTA-pair tiles (128 FLOP/B) win whenever the wave quantisation allows them
-  const double unit_cost[5] = {0.50, 0.50, 0.53, 0.52, 0.41};
+  const double unit_cost[5] = {0.50, 0.48, 0.53, 0.52, 0.41};
   TileCfg best = cands[3];
   double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
