@@ -265,6 +265,22 @@ def run_cuda(args):
         L.ir_profile_end(ms, fl, cnt)
         prof = {"gemm": (ms[0], fl[0], cnt[0]), "conv": (ms[1], fl[1], cnt[1]), "attention": (ms[2], fl[2], cnt[2])}
     peak_tf, peak_hbm, peak_src = _peaks()
+    # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture (profiles/)
+    traffic = None
+    try:
+        import csv
+        with open(ROOT / "profiles" / "r01_ncu_full_gemm_attn_final_summary.csv") as f:
+            rows = list(csv.reader(f))
+        hdr, units = rows[0], rows[1]
+        ir_, iw_, in_ = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir_]) * scale.get(units[ir_], 1.0) + float(r[iw_]) * scale.get(units[iw_], 1.0)
+                for r in rows[2:] if "gemm_tc_kernel" in r[in_]]
+        if vals:
+            traffic = {"dram_bytes_per_launch_avg": sum(vals) / len(vals), "launches_sampled": len(vals),
+                       "source": "profiles/r01_ncu_full_gemm_attn_final_summary.csv (DiT linear launches of one 1024x1024 step)"}
+    except Exception:
+        traffic = None
     roofline = None
     kernels = None
     if prof:
@@ -273,7 +289,7 @@ def run_cuda(args):
         g_n = prof["gemm"][2] + prof["conv"][2]
         ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
                     "launches": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
                     "share_of_step": g_ms / args.steps / (total_ms / args.steps)}
         kernels = {k: {"ms_per_step": v[0] / args.steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12) if v[0] > 0 else None,

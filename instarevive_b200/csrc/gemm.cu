@@ -21,7 +21,7 @@ static constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
 static constexpr int CONV_BW = 16;   // conv tile: 16 x 8 output pixels
 static constexpr int CONV_BH = 8;
 static constexpr int STG_LD = 36;    // staging row stride in floats (32 + 4 pad: conflict-free v4 stores)
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS_MAX = 384;
 
 template <int BN, int CG, bool CONV>
 struct GemmCfg {
@@ -35,7 +35,11 @@ struct GemmCfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_TAP_BYTES = B_ROWS * BK * 2;
   static constexpr int B_BYTES = (CONV ? 3 : 1) * B_TAP_BYTES;
-  static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+  // epilogue warps: 4 for the conv pipeline (no shared memory to spare), 8 for plain GEMMs (two per TMEM lane quarter,
+  // interleaved 32-column chunks): the residual / scatter epilogues are latency-bound, more warps = more loads in flight
+  static constexpr int EW = CONV ? 4 : 8;
+  static constexpr int NUM_THREADS = 128 + 32 * EW;
+  static constexpr int STG_BYTES = EW * 32 * STG_LD * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_MAX = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
@@ -77,7 +81,7 @@ struct GemmDev {
 };
 
 template <int BN, int EPI, bool CONV, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS_MAX, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
   using Cfg = GemmCfg<BN, CG, CONV>;
   constexpr int STAGES = Cfg::STAGES;
@@ -110,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4 * CG);  // epilogue warps of every CTA of the pair release the accumulator
+      mbar_init(&tempty_bar[i], Cfg::EW * CG);  // epilogue warps of every CTA of the pair release the accumulator
     }
     fence_mbar_init();
   }
@@ -251,15 +255,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
-    const int q = warp - 4;  // TMEM lane quarter: lanes [32q, 32q+32)
-    float* stg = staging + q * (32 * STG_LD);
+    constexpr int EW = Cfg::EW;
+    constexpr int CSTEP = EW / 4;           // warps per TMEM lane quarter = chunk interleave
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
+    const int chalf = (warp - 4) >> 2;      // which interleaved set of 32-column chunks this warp owns
+    float* stg = staging + (warp - 4) * (32 * STG_LD);
     const uint32_t stg_s = smem_u32(stg);
     const int col4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
     // fused GroupNorm statistics: per-lane (sum, sum of squares) of its 4 channels per 32-column chunk over the rows of
     // ONE tile, reduced by a fixed shuffle tree and written to the slot of (image, tile, warp). Per-tile partials do not
     // depend on how tiles are scheduled or batched, so the statistics are bit-reproducible for any sharding.
-    float gn_s[BN / 32], gn_q[BN / 32];
+    float gn_s[BN / 32 / CSTEP], gn_q[BN / 32 / CSTEP];
     const bool gn_on = (EPI == EPI_BF16) && p.gn_partial != nullptr;
     int it = 0;
     for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
@@ -271,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t use = (uint32_t)(it >> 1);
       if (gn_on) {
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 32 / CSTEP; ++c) {
           gn_s[c] = 0.f;
           gn_q[c] = 0.f;
         }
@@ -318,11 +325,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       };
-      if (EPI == EPI_F32 || EPI == EPI_BF16) load_resid(0, res_cur, resb_cur);
+      if (EPI == EPI_F32 || EPI == EPI_BF16) load_resid(chalf, res_cur, resb_cur);
       const bool gate_uniform = gate_row[0] == gate_row[7];
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf; c < BN / 32; c += CSTEP) {
+        const bool last_chunk = c + CSTEP >= BN / 32;
         if (EPI == EPI_QKV) {
           // head-major scatter of the qkv projection; D1 = H*hd is a multiple of 32, so a chunk is all-q, all-k or all-v
           const int D1 = p.qkv_H * p.qkv_hd;
@@ -330,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
           tmem_ld_wait();
-          if (c == BN / 32 - 1) {
+          if (last_chunk) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -412,7 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4 gate4[8];
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float chunk_s = 0.f, chunk_q = 0.f;
-        if (c + 1 < BN / 32 && (EPI == EPI_F32 || EPI == EPI_BF16)) load_resid(c + 1, res_nxt, resb_nxt);
+        if (!last_chunk && (EPI == EPI_F32 || EPI == EPI_BF16)) load_resid(c + CSTEP, res_nxt, resb_nxt);
         if (col_ok) {
           if (p.bias) bias4 = *reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + col);
           if (EPI == EPI_F32) {
@@ -434,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), v);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (last_chunk) {
           // accumulator fully read: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -496,8 +504,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (gn_on) {
 #pragma unroll
-          for (int cc = 0; cc < BN / 32; ++cc) {   // static indexing keeps the accumulators in registers
-            if (cc == c) {
+          for (int cc = 0; cc < BN / 32 / CSTEP; ++cc) {   // static indexing keeps the accumulators in registers
+            if (cc == c / CSTEP) {
               gn_s[cc] += chunk_s;
               gn_q[cc] += chunk_q;
             }
@@ -517,8 +525,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tile_in_img = CONV ? m_blk : m_blk - img * tiles_per_img;
         const int gpc = 32 / p.gn_cpg;   // groups per 32-column chunk
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          float s_ = gn_s[c], q_ = gn_q[c];
+        for (int lc = 0; lc < BN / 32 / CSTEP; ++lc) {
+          const int c = lc * CSTEP + chalf;   // global 32-column chunk index of this warp's lc-th chunk
+          float s_ = gn_s[lc], q_ = gn_q[lc];
           s_ += __shfl_xor_sync(0xffffffffu, s_, 8);
           q_ += __shfl_xor_sync(0xffffffffu, q_, 8);
           s_ += __shfl_xor_sync(0xffffffffu, s_, 16);
@@ -536,17 +545,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stg_s + (uint32_t)gi * 8u), "f"(s_), "f"(q_) : "memory");
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q == 0 && m_blk < p.m_blocks) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        if (warp == 4 && m_blk < p.m_blocks) {
           const uint32_t stg0 = smem_u32(staging);
           for (int gi = lane; gi < (BN / 32) * gpc; gi += 32) {
             const int gcol = n_blk * BN + gi * p.gn_cpg;
             if (gcol < p.N) {
+              // the group lives in chunk gi / gpc, owned by column-set (chunk % CSTEP): sum its 4 lane-quarter warps
+              const int owner = (gi / gpc) % CSTEP;
               float s_ = 0.f, q_ = 0.f;
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
                 float a0, a1;
-                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0), "=f"(a1) : "r"(stg0 + (uint32_t)(w * 32 * STG_LD * 4 + gi * 8)) : "memory");
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0), "=f"(a1)
+                             : "r"(stg0 + (uint32_t)((owner * 4 + w) * 32 * STG_LD * 4 + gi * 8)) : "memory");
                 s_ += a0;
                 q_ += a1;
               }
@@ -555,7 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging is reused by the next tile's first chunk
+        asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // staging is reused by the next tile's first chunk
       }
     }
   }
@@ -651,7 +663,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
   const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
