@@ -157,6 +157,9 @@ int ir_gemm_qkv_heads(const void* A, const void* W, const float* bias, int M, in
 /* tcgen05 self-attention on head-major operands (see ir_gemm_qkv_heads); out: (B*T, ldo) bf16. */
 int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* vt_heads, void* out, long long ldo, int B,
                          int H, int head_dim, int T, int Tp, float scale, void* stream);
+/* Diagnostics: with a device buffer of the returned length (int64 elements) set, ir_attention_tc_bf16 runs an
+ * instrumented instantiation that records SM-clock stamps of the warp roles of CTA (0,0,0); NULL switches it off. */
+int ir_debug_attention_trace(long long* device_buf);
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream);
 int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream);

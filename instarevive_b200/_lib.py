@@ -46,6 +46,7 @@ PROTOTYPES = {
     "ir_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp]),
     "ir_gemm_qkv_heads": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "ir_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp]),
+    "ir_debug_attention_trace": (_i, [_vp]),
     "ir_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ir_pos_embed": (_i, [_vp, _i, _i, _i, _i, _f, _vp]),
     "ir_vae_create": (_i, [C.POINTER(VaeConfig), C.POINTER(_vp)]),

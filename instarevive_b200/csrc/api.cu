@@ -415,6 +415,11 @@ int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* v
   return attention_tc_launch(a, (cudaStream_t)stream);
 }
 
+int ir_debug_attention_trace(long long* device_buf) {
+  attention_tc_set_trace(device_buf);
+  return attention_tc_trace_len();
+}
+
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream) {
   return ln_modulate_launch(x, (bf16*)out_bf16, shift, scale, mod_stride, rows, T, D, (cudaStream_t)stream);

@@ -32,5 +32,9 @@ struct AttnTcArgs {
   float scale = 1.0f;
 };
 int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream);
+// diagnostics: when a device buffer of attention_tc_trace_len() int64 is set, attention_tc_launch runs the instrumented
+// instantiation, which records SM-clock stamps of the roles of CTA (0,0,0) (tools/gpu_attn_probe.py --trace)
+void attention_tc_set_trace(long long* device_buf);
+int attention_tc_trace_len();
 
 }  // namespace ir

@@ -3,11 +3,18 @@
 //
 // One CTA owns 256 query rows of one (sample, head) as two 128-row tiles that ping-pong on the tensor core:
 //   warp 0      TMA producer: Q tiles once, then a ring of K / V^T tiles (128 keys each)
-//   warp 1      MMA issuer (one thread): S_q = Q_q K^T into TMEM, O_q += P_q V into TMEM
-//   warps 2-5   softmax of query tile 0, warps 6-9 softmax of query tile 1 (one thread per query row, no shuffles):
+//   warps 1, 2  MMA issuers (one thread each), one per query tile: S_q = Q_q K^T into TMEM, O_q += P_q V into TMEM.
+//               Each issuer follows its own query tile's barriers in program order (blocking mbarrier waits, which
+//               sleep in hardware and wake within ~60 cycles of the arrive), so neither tile ever waits on the other.
+//   warp 3      idle (keeps the softmax warps warpgroup-aligned for setmaxnreg)
+//   warps 4-7   softmax of query tile 0, warps 8-11 softmax of query tile 1 (one thread per query row, no shuffles):
 //               tcgen05.ld the S row, online max with lazy rescaling of the O accumulator (tcgen05.ld/st, only when the
 //               running max grew by more than 2^8), exp2, bf16 P written to shared memory in the 128B-swizzled K-major
-//               layout the P*V MMA consumes.
+//               layout the P*V MMA consumes. The softmax is MUFU-bound at head_dim 72 (128 ex2 per row and tile against
+//               ~1300 tensor cycles), so the row math uses packed FFMA2 / FADD2 and a compile-time fraction of the
+//               exponentials is evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative
+//               error 7.5e-5, far below the bf16 rounding of P). setmaxnreg moves registers from warps 0-3 to the
+//               softmax warps (S row = 128 live registers).
 // head_dim 72 is handled without padding the data in HBM: q / k are stored head-major [B][H][T][72] and v transposed
 // [B][H][72][Tp] by the qkv GEMM epilogue (EPI_QKV); TMA boxes read 64 + 16 columns and the tensor-map bounds make the
 // hardware zero-fill columns 72..79 (and keys / rows beyond T), so QK^T runs 5 k-steps of 16 and P*V is an N = 80 MMA.
@@ -31,7 +38,11 @@ constexpr int VT_ATOM_BYTES = NV * 64 * 2;  // 10240: [80 rows (d)][64 keys]
 constexpr int STAGE_BYTES = K64_BYTES + K16_BYTES + 2 * VT_ATOM_BYTES;  // 40960
 constexpr int P_BYTES = BQ * BKV * 2;     // 32768: two [128][64] atoms
 constexpr int SMEM_BYTES = 1024 + 2 * QTILE_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + 256;
-constexpr int NTHREADS = 320;   // warp 0 TMA (+TMEM alloc), warp 1 MMA, warps 2-9 softmax (2 query tiles x 4 lane quarters)
+constexpr int NTHREADS = 384;   // warp 0 TMA (+TMEM alloc), warps 1-2 MMA, warp 3 idle, warps 4-11 softmax (2 tiles x 4 lane quarters)
+// setmaxnreg moves registers inside the CTA's launch allocation (384 threads x 168 = 64512 registers), so
+// 128 * REGS_CTRL + 256 * REGS_SOFTMAX must not exceed that or the last setmaxnreg.inc never returns.
+constexpr int REGS_CTRL = 48, REGS_SOFTMAX = 224;
+static_assert(128 * REGS_CTRL + 256 * REGS_SOFTMAX <= NTHREADS * 168, "setmaxnreg budget");
 constexpr int TMEM_S0 = 0, TMEM_S1 = 128, TMEM_O0 = 256, TMEM_O1 = 384;
 
 struct AttnTcDev {
@@ -40,7 +51,10 @@ struct AttnTcDev {
   int T;        // tokens per sample (queries = keys)
   int H;
   float scale_log2e;
+  float inv_scale_log2e;
+  long long* trace;   // diagnostics (TRACE instantiation only): [4 roles][TRACE_ITERS][8] SM-clock stamps of CTA (0,0,0)
 };
+constexpr int TRACE_ITERS = 64;
 
 IR_DEVINL float fast_exp2(float x) {
   float y;
@@ -48,8 +62,56 @@ IR_DEVINL float fast_exp2(float x) {
   return y;
 }
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue once for two lanes of data)
+IR_DEVINL uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+IR_DEVINL void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+IR_DEVINL uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+IR_DEVINL uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+template <int N>
+IR_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+IR_DEVINL void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// 2^x for a packed pair on the FMA pipe. x must be >= -126 (callers clamp the scores) and < 2^21.
+// t = x + 1.5*2^23 rounds x to the nearest integer n and leaves n in the low mantissa bits of t; f = x - n in
+// [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial; the exponent is applied by adding n << 23 to the bit pattern.
+IR_DEVINL void exp2_poly2(uint64_t x, float& e0, float& e1) {
+  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const uint64_t neg1 = pack2(-1.f, -1.f);
+  const uint64_t c0 = pack2(0.9999280571937561f, 0.9999280571937561f), c1 = pack2(0.6932609677314758f, 0.6932609677314758f);
+  const uint64_t c2 = pack2(0.24261091649532318f, 0.24261091649532318f), c3 = pack2(0.05517148599028587f, 0.05517148599028587f);
+  const uint64_t t = add2(x, magic);
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t f = fma2(n, neg1, x);
+  uint64_t p = fma2(f, c3, c2);
+  p = fma2(p, f, c1);
+  p = fma2(p, f, c0);
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 }  // namespace
 
+// EMU8: of every 8 consecutive key pairs, EMU8 are exponentiated on the FMA pipe instead of the MUFU (0..4).
+// ORDER > 0: the exponential sections of the two query tiles take turns (token passing through two mbarriers), which
+// keeps the tiles in anti-phase: one tile's MUFU section runs against the other tile's TMEM load / row max / P store /
+// MMAs. The token is handed over after ORDER of the 4 column chunks of the row (4 = strictly exclusive sections).
+template <int EMU8, int ORDER, bool TRACE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
                const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
@@ -57,23 +119,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // [2][Q64 | Q16]
-  uint8_t* sKV = sQ + 2 * QTILE_BYTES;                 // [STAGES][K64 | K16 | VT0 | VT1]
+  uint8_t* sKV = sQ + 2 * QTILE_BYTES;                 // [STAGES][K64 | K16 | VT0 | VT1]; K and V^T rings run separately
   uint8_t* sP = sKV + STAGES * STAGE_BYTES;            // [2][P atom0 | P atom1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars;                  // [1]
-  uint64_t* kv_full = bars + 1;             // [STAGES]
-  uint64_t* kv_empty = bars + 1 + STAGES;   // [STAGES]
-  uint64_t* s_full = bars + 1 + 2 * STAGES;   // [2]
+  uint64_t* q_full = bars;                    // [1]
+  uint64_t* k_full = q_full + 1;              // [STAGES]
+  uint64_t* k_empty = k_full + STAGES;        // [STAGES] both S = Q K^T of the tile have retired
+  uint64_t* v_full = k_empty + STAGES;        // [STAGES]
+  uint64_t* v_empty = v_full + STAGES;        // [STAGES] both P V of the tile have retired
+  uint64_t* s_full = v_empty + STAGES;        // [2]
   uint64_t* p_full = s_full + 2;              // [2]
   uint64_t* o_full = p_full + 2;              // [2]
   uint64_t* s_free = o_full + 2;              // [2] softmax has copied S into registers: S buffer may be overwritten
   uint64_t* pv_done = s_free + 2;             // [2] P*V of the previous tile finished: P smem / O TMEM may be touched
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* order = pv_done + 2;              // [2] order[t]: query tile t may run its exponential section
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(order + 2);
+  static_assert((1 + 4 * STAGES + 12) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ;
   const int head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.T + BKV - 1) / BKV;
+  const bool tracing = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  auto stamp = [&](int role, int iter, int slot) {
+    if (TRACE && tracing && iter < TRACE_ITERS) p.trace[(role * TRACE_ITERS + iter) * 8 + slot] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ64);
@@ -85,8 +155,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -94,6 +166,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       mbar_init(&o_full[i], 1);
       mbar_init(&s_free[i], BQ);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&order[i], BQ);
     }
     fence_mbar_init();
   }
@@ -109,36 +182,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   pdl_wait();
   pdl_launch();
 
+  // setmaxnreg sits at the top of each role branch (ptxas budgets registers per branch from it)
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<REGS_CTRL>();
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * QTILE_BYTES);
       for (int qt = 0; qt < 2; ++qt) {
         tma_load_4d(sQ + qt * QTILE_BYTES, &tmQ64, q_full, 0, q0 + qt * BQ, head, b);
         tma_load_4d(sQ + qt * QTILE_BYTES + Q64_BYTES, &tmQ16, q_full, 64, q0 + qt * BQ, head, b);
       }
+      // K runs two tiles ahead of V (S(j+2) is issued while P V(j) is pending), so the two rings have their own
+      // barriers: the K slot of tile j is free as soon as both S(j) retired, long before the V slot.
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* st = sKV + stage * STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], STAGE_BYTES);
-        tma_load_4d(st, &tmK64, &kv_full[stage], 0, j * BKV, head, b);
-        tma_load_4d(st + K64_BYTES, &tmK16, &kv_full[stage], 64, j * BKV, head, b);
-        tma_load_4d(st + K64_BYTES + K16_BYTES, &tmVT, &kv_full[stage], j * BKV, 0, head, b);
-        tma_load_4d(st + K64_BYTES + K16_BYTES + VT_ATOM_BYTES, &tmVT, &kv_full[stage], j * BKV + 64, 0, head, b);
+      for (int j = 0; j < n_tiles + 2; ++j) {
+        if (j < n_tiles) {
+          mbar_wait(&k_empty[stage], phase ^ 1);
+          uint8_t* st = sKV + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&k_full[stage], K64_BYTES + K16_BYTES);
+          tma_load_4d(st, &tmK64, &k_full[stage], 0, j * BKV, head, b);
+          tma_load_4d(st + K64_BYTES, &tmK16, &k_full[stage], 64, j * BKV, head, b);
+        }
+        if (j >= 2) {   // V(j-2): stage index and phase lag the K ring by two tiles
+          const int jv = j - 2;
+          const int vs = jv % STAGES;
+          const uint32_t vp = (uint32_t)((jv / STAGES) & 1);
+          mbar_wait(&v_empty[vs], vp ^ 1);
+          uint8_t* st = sKV + vs * STAGE_BYTES + K64_BYTES + K16_BYTES;
+          mbar_arrive_expect_tx(&v_full[vs], 2 * VT_ATOM_BYTES);
+          tma_load_4d(st, &tmVT, &v_full[vs], jv * BKV, 0, head, b);
+          tma_load_4d(st + VT_ATOM_BYTES, &tmVT, &v_full[vs], jv * BKV + 64, 0, head, b);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ MMA issuer (warp 1, one thread)
+    setmaxnreg_dec<REGS_CTRL>();
+    if (warp == 1 && lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, NV);
-      auto issue_s = [&](int qt, int stage) {
+      auto issue_s = [&](int qt, int t) {   // S_qt(t) = Q_qt K(t)^T; waits for K(t) and for the S buffer
+        const int stage = t % STAGES;
+        mbar_wait(&k_full[stage], (uint32_t)((t / STAGES) & 1));
+        if (t > 0) mbar_wait(&s_free[qt], (uint32_t)((t - 1) & 1));
+        tc_fence_after();
         const uint32_t qa = smem_u32(sQ + qt * QTILE_BYTES);
         const uint32_t ka = smem_u32(sKV + stage * STAGE_BYTES);
         const uint64_t dq = make_smem_desc_sw128(qa), dk = make_smem_desc_sw128(ka);
@@ -147,8 +239,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
         for (int k = 0; k < 4; ++k) umma_bf16(td, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
         umma_bf16(td, make_smem_desc_sw32(qa + Q64_BYTES), make_smem_desc_sw32(ka + K64_BYTES), idesc_s, 1);
         umma_commit(&s_full[qt]);
+        if (qt == 1) umma_commit(&k_empty[stage]);   // both S of tile t issued: the K slot is free once they retire
       };
-      auto issue_pv = [&](int qt, int stage, bool accumulate) {
+      auto issue_pv = [&](int qt, int t) {   // O_qt += P_qt(t) V(t)
+        const int stage = t % STAGES;
+        if (qt == 0) mbar_wait(&v_full[stage], (uint32_t)((t / STAGES) & 1));
+        mbar_wait(&p_full[qt], (uint32_t)(t & 1));
+        tc_fence_after();
         const uint32_t pa = smem_u32(sP + qt * P_BYTES);
         const uint32_t va = smem_u32(sKV + stage * STAGE_BYTES + K64_BYTES + K16_BYTES);
         const uint32_t td = tmem_base + (qt == 0 ? TMEM_O0 : TMEM_O1);
@@ -156,98 +253,89 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint64_t dp = make_smem_desc_sw128(pa + (kk >> 2) * (BQ * 128)) + (uint64_t)(2 * (kk & 3));
           const uint64_t dv = make_smem_desc_sw128(va + (kk >> 2) * VT_ATOM_BYTES) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(td, dp, dv, idesc_o, (accumulate || kk != 0) ? 1u : 0u);
+          umma_bf16(td, dp, dv, idesc_o, (t > 0 || kk != 0) ? 1u : 0u);
         }
+        if (qt == 1) umma_commit(&v_empty[stage]);
+        if (t + 1 < n_tiles)
+          umma_commit(&pv_done[qt]);     // softmax(qt, t+1) may overwrite P_qt / rescale O_qt once this fires
+        else
+          umma_commit(&o_full[qt]);
       };
+      // Issue order = steady-state order of the events when the two query tiles run in anti-phase:
+      //   P V_0(j), S_0(j+2), P V_1(j), S_1(j+2)   (S runs two tiles ahead: S(j+1) is consumed while P(j) is produced)
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      // Event-driven issue: per query tile, S(t) may go as soon as the softmax warps have copied S(t-1) out of TMEM
-      // (s_free) and K(t) has landed; P*V(t) as soon as P(t) is in shared memory (p_full). Polling both query tiles
-      // keeps the tensor core fed whichever softmax group finishes first.
-      int s_next[2] = {1, 1}, pv_next[2] = {0, 0};
-      int kv_seen = 0;       // tiles [0, kv_seen] have landed
-      int kv_released = 0;   // tiles [0, kv_released) have been handed back to the producer
-      while (pv_next[0] < n_tiles || pv_next[1] < n_tiles) {
-#pragma unroll
+#pragma unroll 1
+      for (int t = 0; t < 2 && t < n_tiles; ++t) {
+#pragma unroll 1
+        for (int qt = 0; qt < 2; ++qt) issue_s(qt, t);
+      }
+#pragma unroll 1
+      for (int j = 0; j < n_tiles; ++j) {
+#pragma unroll 1
         for (int qt = 0; qt < 2; ++qt) {
-          const int ts = s_next[qt];
-          if (ts < n_tiles) {
-            if (ts > kv_seen && mbar_try_wait(&kv_full[ts % STAGES], (uint32_t)((ts / STAGES) & 1))) kv_seen = ts;
-            if (ts <= kv_seen && mbar_try_wait(&s_free[qt], (uint32_t)((ts - 1) & 1))) {
-              tc_fence_after();
-              issue_s(qt, ts % STAGES);
-              s_next[qt] = ts + 1;
-            }
-          }
-          const int tp = pv_next[qt];
-          if (tp < n_tiles && mbar_try_wait(&p_full[qt], (uint32_t)(tp & 1))) {
-            tc_fence_after();
-            issue_pv(qt, tp % STAGES, tp > 0);
-            if (tp + 1 < n_tiles)
-              umma_commit(&pv_done[qt]);   // softmax(qt, tp+1) may overwrite P_qt / rescale O_qt once this fires
-            else
-              umma_commit(&o_full[qt]);
-            pv_next[qt] = tp + 1;
-            const int done = pv_next[0] < pv_next[1] ? pv_next[0] : pv_next[1];
-            while (kv_released < done) {
-              umma_commit(&kv_empty[kv_released % STAGES]);   // both P*V(kv_released) issued: stage can be refilled
-              ++kv_released;
-            }
-          }
+          stamp(2, j, 2 * qt);
+          issue_pv(qt, j);
+          stamp(2, j, 2 * qt + 1);
+          if (j + 2 < n_tiles) issue_s(qt, j + 2);
         }
+        stamp(2, j, 4);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax: one thread per query row
-    const int qt = (warp - 2) >> 2;
+    setmaxnreg_inc<REGS_SOFTMAX>();
+    const int qt = (warp - 4) >> 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;          // row inside the tile == TMEM lane
     const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (qt == 0 ? TMEM_S0 : TMEM_S1);
     const uint32_t t_o = tmem_base + ((uint32_t)(quarter * 32) << 16) + (qt == 0 ? TMEM_O0 : TMEM_O1);
-    uint8_t* prow = sP + qt * P_BYTES + r * 128;
+    const uint32_t prow = smem_u32(sP + qt * P_BYTES + r * 128);
     const int rx = r & 7;
-    float m_used = -INFINITY, l = 0.f;
+    const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
+    float m_used = -INFINITY;
+    uint64_t l2 = pack2(0.f, 0.f);   // running row sum, two partial sums (rescaled together)
     for (int j = 0; j < n_tiles; ++j) {
+      if (quarter == 0) stamp(qt, j, 0);
       mbar_wait(&s_full[qt], (uint32_t)(j & 1));
+      if (quarter == 0) stamp(qt, j, 1);
       tc_fence_after();
       uint32_t s[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_free[qt]);   // S lives in registers now: the tensor core may start S(qt, j+1)
+      mbar_arrive(&s_free[qt]);   // S lives in registers now: the tensor core may start the next S of this tile
+      if (quarter == 0) stamp(qt, j, 2);
       const int kbase = j * BKV;
-      float mx = -INFINITY;
-      if (kbase + BKV <= p.T) {
+      if (kbase + BKV > p.T) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; ++i)
             if (kbase + c * 32 + i >= p.T) s[c][i] = __float_as_uint(-INFINITY);
-            mx = fmaxf(mx, __uint_as_float(s[c][i]));
-          }
       }
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains of 3-input max
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
       const float m_new = fmaxf(m_used, mx * p.scale_log2e);
-      if (j > 0) {
-        // P*V(qt, j-1) must have finished reading P_qt and accumulating into O_qt before either is touched again
-        mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
+      if (quarter == 0) stamp(qt, j, 3);
       // lazy rescale: keep the stale max unless it grew by more than 8 (p stays below 2^8, exact in fp32 / fine in bf16)
       const bool grow = (m_new - m_used) > 8.0f;   // also true on the first tile (m_used = -inf)
+      bool pv_waited = (j == 0);
       if (__any_sync(0xffffffffu, grow)) {
         const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
         if (grow) m_used = m_new;
-        l *= alpha;
+        const uint64_t alpha2 = pack2(alpha, alpha);
+        l2 = fma2(l2, alpha2, pack2(0.f, 0.f));
         if (j > 0) {
+          // P*V(qt, j-1) must have finished accumulating into O_qt before it is rescaled
+          mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+          pv_waited = true;
 #pragma unroll
           for (int c = 0; c < NV / 16; ++c) {
             uint32_t o[16];
@@ -260,28 +348,66 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
           tmem_st_wait();
         }
       }
-      float sum = 0.f;
+      const uint64_t negm2 = pack2(-m_used, -m_used);
+      // scores whose exponent would fall below 2^-120 are clamped there (only the polynomial path needs it)
+      const float s_lo = (m_used - 120.0f) * p.inv_scale_log2e;
+      uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
+      if (ORDER) mbar_wait(&order[qt], (uint32_t)((j & 1) ^ (qt == 0 ? 1 : 0)));   // tile 0's first turn is free
+      if (quarter == 0) stamp(qt, j, 4);
+      uint32_t pk[64];   // P row as packed bf16 pairs: kept in registers until P*V(j-1) has released the P buffer
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = fast_exp2(__uint_as_float(s[c][g * 8 + i]) * p.scale_log2e - m_used);
-            sum += e[i];
+          for (int pr = 0; pr < 4; ++pr) {
+            const int pi = (g & 1) * 4 + pr;                 // pair index inside a 16-key window
+            const bool emulate = ((pi * EMU8) & 7) < EMU8;   // spreads EMU8 emulated pairs over the window
+            float s0 = __uint_as_float(s[c][g * 8 + 2 * pr]), s1 = __uint_as_float(s[c][g * 8 + 2 * pr + 1]);
+            if (emulate) {
+              s0 = fmaxf(s0, s_lo);
+              s1 = fmaxf(s1, s_lo);
+            }
+            const uint64_t x = fma2(pack2(s0, s1), scale2, negm2);
+            float e0, e1;
+            if (emulate) {
+              exp2_poly2(x, e0, e1);
+            } else {
+              float x0, x1;
+              unpack2(x, x0, x1);
+              e0 = fast_exp2(x0);
+              e1 = fast_exp2(x1);
+            }
+            if (pr & 1)
+              sum_b = add2(sum_b, pack2(e0, e1));
+            else
+              sum_a = add2(sum_a, pack2(e0, e1));
+            pk[c * 16 + g * 4 + pr] = pack_bf16x2(e0, e1);
           }
-          const int jc = c * 4 + g;   // 16-byte chunk (8 keys) index inside the 128-key row
-          uint4 u = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                               pack_bf16x2(e[6], e[7]));
-          *reinterpret_cast<uint4*>(prow + (jc >> 3) * (BQ * 128) + (((jc & 7) ^ rx) << 4)) = u;
         }
+        if (ORDER > 0 && c == ORDER - 1) mbar_arrive(&order[qt ^ 1]);   // hand the MUFU over
       }
-      l += sum;
+      l2 = add2(l2, add2(sum_a, sum_b));
+      if (quarter == 0) stamp(qt, j, 5);
+      if (!pv_waited) {
+        // P*V(qt, j-1) must have finished reading P_qt before it is overwritten
+        mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
+      }
+#pragma unroll
+      for (int jc = 0; jc < 16; ++jc) {   // 16-byte chunks (8 keys) of the 128-key row, 128B-swizzled K-major
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)((jc >> 3) * (BQ * 128)) +
+                                                                      (uint32_t)(((jc & 7) ^ rx) << 4)),
+                     "r"(pk[jc * 4]), "r"(pk[jc * 4 + 1]), "r"(pk[jc * 4 + 2]), "r"(pk[jc * 4 + 3])
+                     : "memory");
+      }
       fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(&p_full[qt]);
+      if (quarter == 0) stamp(qt, j, 6);
     }
+    float l_lo, l_hi;
+    unpack2(l2, l_lo, l_hi);
+    const float l = l_lo + l_hi;
     // ---- epilogue: O / l -> bf16 -> out[(b*T + row)][head*72 + d]
     mbar_wait(&o_full[qt], 0);
     tc_fence_after();
@@ -325,6 +451,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   }
 }
 
+static long long* g_attn_trace = nullptr;
+void attention_tc_set_trace(long long* device_buf) { g_attn_trace = device_buf; }
+int attention_tc_trace_len() { return 4 * TRACE_ITERS * 8; }
+
 int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.head_dim == HD, "attention_tc: head_dim %d unsupported (kernel is specialised for %d)", a.head_dim, HD);
   IR_REQUIRE(a.q && a.k && a.vt && a.out && a.B > 0 && a.H > 0 && a.T > 0, "attention_tc: bad arguments");
@@ -346,22 +476,60 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
     const uint32_t box[4] = {64, NV, 1, 1};
     IR_TRY(make_tensor_map(&mvt, a.vt, 4, dims, strides, box, 128));
   }
-  static bool configured = false;
-  if (!configured) {
-    IR_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
   AttnTcDev p;
   p.out = a.out;
   p.ldo = a.ldo;
   p.T = a.T;
   p.H = a.H;
   p.scale_log2e = a.scale * 1.4426950408889634f;
+  p.inv_scale_log2e = 1.0f / p.scale_log2e;
+  p.trace = g_attn_trace;
   dim3 grid((a.T + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-  const bool prof = prof_enabled();
-  if (prof) prof_before(stream);
-  IR_CUDA_CHECK(launch_pdl(attn_tc_kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mq64, mq16, mk64, mk16, mvt, p));
-  if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD);
+  // share of the exponentials evaluated on the FMA pipe: EMU8 of every 8 key pairs. 2 (25 %) balances the MUFU and
+  // issue-slot budgets of the softmax warps; IR_ATTN_EMU overrides it for measurements (tools/gpu_attn_probe.py).
+  static const int emu = [] {
+    const char* e = getenv("IR_ATTN_EMU");
+    const int v = e ? atoi(e) : 2;
+    return v < 0 ? 0 : (v > 4 ? 4 : v);
+  }();
+  auto launch = [&](auto kernel) -> int {
+    static bool configured = false;   // one static per kernel instantiation (the lambda body is instantiated per type)
+    if (!configured) {
+      IR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      configured = true;
+    }
+    const bool prof = prof_enabled();
+    if (prof) prof_before(stream);
+    IR_CUDA_CHECK(launch_pdl(kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mq64, mq16, mk64, mk16, mvt, p));
+    if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD);
+    return IR_OK;
+  };
+  static const int order = [] {
+    const char* e = getenv("IR_ATTN_ORDER");
+    const int v = e ? atoi(e) : 3;
+    return v < 0 ? 0 : (v > 4 ? 4 : v);
+  }();
+  if (g_attn_trace) {
+    switch (order) {
+      case 0: return launch(attn_tc_kernel<2, 0, true>);
+      case 3: return launch(attn_tc_kernel<2, 3, true>);
+      default: return launch(attn_tc_kernel<2, 4, true>);
+    }
+  }
+  const int key = order * 10 + emu;
+  switch (key) {
+    case 0: IR_TRY(launch(attn_tc_kernel<0, 0>)); break;
+    case 2: IR_TRY(launch(attn_tc_kernel<2, 0>)); break;
+    case 30: IR_TRY(launch(attn_tc_kernel<0, 3>)); break;
+    case 32: IR_TRY(launch(attn_tc_kernel<2, 3>)); break;
+    case 33: IR_TRY(launch(attn_tc_kernel<3, 3>)); break;
+    case 34: IR_TRY(launch(attn_tc_kernel<4, 3>)); break;
+    case 40: IR_TRY(launch(attn_tc_kernel<0, 4>)); break;
+    case 42: IR_TRY(launch(attn_tc_kernel<2, 4>)); break;
+    case 44: IR_TRY(launch(attn_tc_kernel<4, 4>)); break;
+    default:
+      IR_REQUIRE(false, "attention_tc: no instantiation for IR_ATTN_ORDER=%d IR_ATTN_EMU=%d", order, emu);
+  }
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;
