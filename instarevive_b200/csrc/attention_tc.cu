@@ -1,20 +1,21 @@
 // tcgen05 / TMEM flash attention for the DiT self-attention (AttentionKVCompress.forward with sr_ratio 1,
 // diffusion/model/nets/PixArt_blocks.py:123-158: softmax(q k^T / sqrt(72)) v, 16 heads, no mask).
 //
-// One CTA owns 256 query rows of one (sample, head) as two 128-row tiles that ping-pong on the tensor core:
-//   warp 0      TMA producer: Q tiles once, then a ring of K / V^T tiles (128 keys each)
-//   warps 1, 2  MMA issuers (one thread each), one per query tile: S_q = Q_q K^T into TMEM, O_q += P_q V into TMEM.
-//               Each issuer follows its own query tile's barriers in program order (blocking mbarrier waits, which
-//               sleep in hardware and wake within ~60 cycles of the arrive), so neither tile ever waits on the other.
-//   warp 3      idle (keeps the softmax warps warpgroup-aligned for setmaxnreg)
+// One CTA owns 256 query rows of one (sample, head) as two 128-row tiles that alternate on the tensor core.
+// Shared memory holds only the K / V^T ring: a single-CTA SS MMA with N = 128 reads 8 KB of operands per 64-cycle
+// instruction, i.e. the whole 128 B/clk shared-memory port, so both A operands live in TMEM instead (TS MMAs):
+//   Q   written once per CTA into TMEM by the softmax threads (bf16 pairs, 40 columns, d 72..79 zero)
+//   P   written by the softmax threads over the first 64 columns of their own S accumulator (bf16 pairs)
+//   warp 0      TMA producer: rings of K tiles and V^T tiles (128 keys each; separate barriers, K runs one tile ahead)
+//   warp 1      MMA issuer (one thread), program order  P V_0(j), S_0(j+1), P V_1(j), S_1(j+1): the tensor pipe executes
+//               in issue order, so S(j+1) may be queued right behind the P V(j) that still reads P out of the same columns
+//   warps 2-3   idle (keep the softmax warps warpgroup-aligned for setmaxnreg)
 //   warps 4-7   softmax of query tile 0, warps 8-11 softmax of query tile 1 (one thread per query row, no shuffles):
 //               tcgen05.ld the S row, online max with lazy rescaling of the O accumulator (tcgen05.ld/st, only when the
-//               running max grew by more than 2^8), exp2, bf16 P written to shared memory in the 128B-swizzled K-major
-//               layout the P*V MMA consumes. The softmax is MUFU-bound at head_dim 72 (128 ex2 per row and tile against
-//               ~1300 tensor cycles), so the row math uses packed FFMA2 / FADD2 and a compile-time fraction of the
-//               exponentials is evaluated on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative
-//               error 7.5e-5, far below the bf16 rounding of P). setmaxnreg moves registers from warps 0-3 to the
-//               softmax warps (S row = 128 live registers).
+//               running max grew by more than 2^8), exp2 with packed FFMA2 / FADD2 row math (optionally a compile-time
+//               share of the exponentials on the FMA pipe: Cody-Waite split + degree-3 minimax polynomial, relative
+//               error 7.5e-5, far below the bf16 rounding of P), tcgen05.st of the bf16 P row.
+// setmaxnreg moves registers from warps 0-3 to the softmax warps (S row = 128 live registers).
 // head_dim 72 is handled without padding the data in HBM: q / k are stored head-major [B][H][T][72] and v transposed
 // [B][H][72][Tp] by the qkv GEMM epilogue (EPI_QKV); TMA boxes read 64 + 16 columns and the tensor-map bounds make the
 // hardware zero-fill columns 72..79 (and keys / rows beyond T), so QK^T runs 5 k-steps of 16 and P*V is an N = 80 MMA.
@@ -28,24 +29,22 @@ constexpr int HD = 72;
 constexpr int BQ = 128;          // rows per query tile (UMMA M)
 constexpr int BKV = 128;         // keys per tile (UMMA N of S, K of P*V)
 constexpr int NV = 80;           // head dim padded to a multiple of 16 (UMMA N of P*V)
-constexpr int STAGES = 3;
-constexpr int Q64_BYTES = BQ * 64 * 2;    // 16384
-constexpr int Q16_BYTES = BQ * 16 * 2;    // 4096
-constexpr int QTILE_BYTES = Q64_BYTES + Q16_BYTES;
+constexpr int STAGES = 4;
 constexpr int K64_BYTES = BKV * 64 * 2;   // 16384
 constexpr int K16_BYTES = BKV * 16 * 2;   // 4096
 constexpr int VT_ATOM_BYTES = NV * 64 * 2;  // 10240: [80 rows (d)][64 keys]
 constexpr int STAGE_BYTES = K64_BYTES + K16_BYTES + 2 * VT_ATOM_BYTES;  // 40960
-constexpr int P_BYTES = BQ * BKV * 2;     // 32768: two [128][64] atoms
-constexpr int SMEM_BYTES = 1024 + 2 * QTILE_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + 256;
-constexpr int NTHREADS = 384;   // warp 0 TMA (+TMEM alloc), warps 1-2 MMA, warp 3 idle, warps 4-11 softmax (2 tiles x 4 lane quarters)
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+constexpr int NTHREADS = 384;   // warp 0 TMA (+TMEM alloc), warp 1 MMA, warps 2-3 idle, warps 4-11 softmax (2 tiles x 4 lane quarters)
 // setmaxnreg moves registers inside the CTA's launch allocation (384 threads x 168 = 64512 registers), so
 // 128 * REGS_CTRL + 256 * REGS_SOFTMAX must not exceed that or the last setmaxnreg.inc never returns.
 constexpr int REGS_CTRL = 48, REGS_SOFTMAX = 224;
 static_assert(128 * REGS_CTRL + 256 * REGS_SOFTMAX <= NTHREADS * 168, "setmaxnreg budget");
-constexpr int TMEM_S0 = 0, TMEM_S1 = 128, TMEM_O0 = 256, TMEM_O1 = 384;
+// TMEM columns: S (fp32, P aliased over its first 64 columns), O (fp32, 80 of them), Q (bf16 pairs, 40 used of 48)
+constexpr int TMEM_S0 = 0, TMEM_S1 = 128, TMEM_O0 = 256, TMEM_O1 = 336, TMEM_Q0 = 416, TMEM_Q1 = 464;
 
 struct AttnTcDev {
+  const bf16* q;   // [B][H][T][72]
   bf16* out;
   long ldo;
   int T;        // tokens per sample (queries = keys)
@@ -79,6 +78,11 @@ IR_DEVINL uint64_t add2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+IR_DEVINL bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 template <int N>
 IR_DEVINL void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -107,53 +111,59 @@ IR_DEVINL void exp2_poly2(uint64_t x, float& e0, float& e1) {
 
 }  // namespace
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (bf16 pairs, one row per lane, 8 columns per k-step of 16) stays in TMEM
+IR_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // EMU8: of every 8 consecutive key pairs, EMU8 are exponentiated on the FMA pipe instead of the MUFU (0..4).
-// ORDER > 0: the exponential sections of the two query tiles take turns (token passing through two mbarriers), which
-// keeps the tiles in anti-phase: one tile's MUFU section runs against the other tile's TMEM load / row max / P store /
-// MMAs. The token is handed over after ORDER of the 4 column chunks of the row (4 = strictly exclusive sections).
+// ORDER > 0: the exponential sections of the two query tiles take turns (token passing through two mbarriers): one
+// tile's MUFU section runs against the other tile's TMEM load / row max / MMAs. The token is handed over after ORDER
+// of the 4 column chunks of the row (4 = strictly exclusive sections).
 template <int EMU8, int ORDER, bool TRACE = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant__ CUtensorMap tmQ16,
-               const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
                const __grid_constant__ CUtensorMap tmVT, const AttnTcDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                  // [2][Q64 | Q16]
-  uint8_t* sKV = sQ + 2 * QTILE_BYTES;                 // [STAGES][K64 | K16 | VT0 | VT1]; K and V^T rings run separately
-  uint8_t* sP = sKV + STAGES * STAGE_BYTES;            // [2][P atom0 | P atom1]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars;                    // [1]
-  uint64_t* k_full = q_full + 1;              // [STAGES]
+  uint8_t* sKV = smem;                                 // [STAGES][K64 | K16 | VT0 | VT1]; K and V^T rings run separately
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * STAGE_BYTES);
+  uint64_t* k_full = bars;                    // [STAGES]
   uint64_t* k_empty = k_full + STAGES;        // [STAGES] both S = Q K^T of the tile have retired
   uint64_t* v_full = k_empty + STAGES;        // [STAGES]
   uint64_t* v_empty = v_full + STAGES;        // [STAGES] both P V of the tile have retired
-  uint64_t* s_full = v_empty + STAGES;        // [2]
-  uint64_t* p_full = s_full + 2;              // [2]
+  uint64_t* q_ready = v_empty + STAGES;       // [2] the query tile's rows are in TMEM
+  uint64_t* s_full = q_ready + 2;             // [2] S(j) complete (which implies P V(j-1) complete: in-order pipe)
+  uint64_t* p_full = s_full + 2;              // [2] P(j) is in TMEM
   uint64_t* o_full = p_full + 2;              // [2]
-  uint64_t* s_free = o_full + 2;              // [2] softmax has copied S into registers: S buffer may be overwritten
-  uint64_t* pv_done = s_free + 2;             // [2] P*V of the previous tile finished: P smem / O TMEM may be touched
-  uint64_t* order = pv_done + 2;              // [2] order[t]: query tile t may run its exponential section
+  uint64_t* order = o_full + 2;               // [2] order[t]: query tile t may run its exponential section
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(order + 2);
-  static_assert((1 + 4 * STAGES + 12) * 8 + 4 <= 256, "barrier block");
+  static_assert((4 * STAGES + 10) * 8 + 4 <= 256, "barrier block");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below are convergent and the compiler
+  // emits the uniform-datapath instructions (UTCHMMA / UTMALDG / UTCBAR) directly instead of an elect-one loop around
+  // each of them (which costs ~80 cycles per MMA when the issuing code sits under a divergent `lane == 0`)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ;
   const int head = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.T + BKV - 1) / BKV;
-  const bool tracing = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const bool trace_cta = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool tracing = trace_cta && lane == 0;
   auto stamp = [&](int role, int iter, int slot) {
     if (TRACE && tracing && iter < TRACE_ITERS) p.trace[(role * TRACE_ITERS + iter) * 8 + slot] = clock64();
   };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ64);
-    tma_prefetch_desc(&tmQ16);
     tma_prefetch_desc(&tmK64);
     tma_prefetch_desc(&tmK16);
     tma_prefetch_desc(&tmVT);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -161,11 +171,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_ready[i], BQ);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], BQ);
       mbar_init(&o_full[i], 1);
-      mbar_init(&s_free[i], BQ);
-      mbar_init(&pv_done[i], 1);
       mbar_init(&order[i], BQ);
     }
     fence_mbar_init();
@@ -186,33 +195,35 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     setmaxnreg_dec<REGS_CTRL>();
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * QTILE_BYTES);
-      for (int qt = 0; qt < 2; ++qt) {
-        tma_load_4d(sQ + qt * QTILE_BYTES, &tmQ64, q_full, 0, q0 + qt * BQ, head, b);
-        tma_load_4d(sQ + qt * QTILE_BYTES + Q64_BYTES, &tmQ16, q_full, 64, q0 + qt * BQ, head, b);
-      }
-      // K runs two tiles ahead of V (S(j+2) is issued while P V(j) is pending), so the two rings have their own
-      // barriers: the K slot of tile j is free as soon as both S(j) retired, long before the V slot.
+    const bool leader = elect_one_sync();   // the whole warp runs the loop (convergent), one lane issues
+    {
+      // K runs one tile ahead of V (S(j+1) is queued right behind P V(j)), so the two rings have their own barriers:
+      // the K slot of tile j is free as soon as both S(j) retired, one iteration before the V slot.
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < n_tiles + 2; ++j) {
+      for (int j = 0; j < n_tiles + 1; ++j) {
         if (j < n_tiles) {
           mbar_wait(&k_empty[stage], phase ^ 1);
           uint8_t* st = sKV + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&k_full[stage], K64_BYTES + K16_BYTES);
-          tma_load_4d(st, &tmK64, &k_full[stage], 0, j * BKV, head, b);
-          tma_load_4d(st + K64_BYTES, &tmK16, &k_full[stage], 64, j * BKV, head, b);
+          if (leader) {
+            mbar_arrive_expect_tx(&k_full[stage], K64_BYTES + K16_BYTES);
+            tma_load_4d(st, &tmK64, &k_full[stage], 0, j * BKV, head, b);
+            tma_load_4d(st + K64_BYTES, &tmK16, &k_full[stage], 64, j * BKV, head, b);
+          }
+          __syncwarp();
         }
-        if (j >= 2) {   // V(j-2): stage index and phase lag the K ring by two tiles
-          const int jv = j - 2;
+        if (j >= 1) {   // V(j-1)
+          const int jv = j - 1;
           const int vs = jv % STAGES;
           const uint32_t vp = (uint32_t)((jv / STAGES) & 1);
           mbar_wait(&v_empty[vs], vp ^ 1);
           uint8_t* st = sKV + vs * STAGE_BYTES + K64_BYTES + K16_BYTES;
-          mbar_arrive_expect_tx(&v_full[vs], 2 * VT_ATOM_BYTES);
-          tma_load_4d(st, &tmVT, &v_full[vs], jv * BKV, 0, head, b);
-          tma_load_4d(st + VT_ATOM_BYTES, &tmVT, &v_full[vs], jv * BKV + 64, 0, head, b);
+          if (leader) {
+            mbar_arrive_expect_tx(&v_full[vs], 2 * VT_ATOM_BYTES);
+            tma_load_4d(st, &tmVT, &v_full[vs], jv * BKV, 0, head, b);
+            tma_load_4d(st + VT_ATOM_BYTES, &tmVT, &v_full[vs], jv * BKV + 64, 0, head, b);
+          }
+          __syncwarp();
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -221,64 +232,67 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       }
     }
   } else if (warp < 4) {
-    // ------------------------------------------------------------------ MMA issuer (warp 1, one thread)
+    // ------------------------------------------------------------------ MMA issuer (warp 1: convergent, one lane issues)
     setmaxnreg_dec<REGS_CTRL>();
-    if (warp == 1 && lane == 0) {
+    if (warp == 1) {
+      const bool leader = elect_one_sync();
+      auto istamp = [&](int iter, int slot) {
+        if (TRACE && trace_cta && leader && iter < TRACE_ITERS) p.trace[(2 * TRACE_ITERS + iter) * 8 + slot] = clock64();
+      };
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, NV);
-      auto issue_s = [&](int qt, int t) {   // S_qt(t) = Q_qt K(t)^T; waits for K(t) and for the S buffer
+      auto issue_s = [&](int qt, int t) {   // S_qt(t) = Q_qt K(t)^T, A = Q from TMEM
         const int stage = t % STAGES;
         mbar_wait(&k_full[stage], (uint32_t)((t / STAGES) & 1));
-        if (t > 0) mbar_wait(&s_free[qt], (uint32_t)((t - 1) & 1));
         tc_fence_after();
-        const uint32_t qa = smem_u32(sQ + qt * QTILE_BYTES);
         const uint32_t ka = smem_u32(sKV + stage * STAGE_BYTES);
-        const uint64_t dq = make_smem_desc_sw128(qa), dk = make_smem_desc_sw128(ka);
+        const uint64_t dk = make_smem_desc_sw128(ka);
         const uint32_t td = tmem_base + (qt == 0 ? TMEM_S0 : TMEM_S1);
+        const uint32_t tq = tmem_base + (qt == 0 ? TMEM_Q0 : TMEM_Q1);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(td, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k != 0);
-        umma_bf16(td, make_smem_desc_sw32(qa + Q64_BYTES), make_smem_desc_sw32(ka + K64_BYTES), idesc_s, 1);
-        umma_commit(&s_full[qt]);
-        if (qt == 1) umma_commit(&k_empty[stage]);   // both S of tile t issued: the K slot is free once they retire
+          for (int k = 0; k < 4; ++k) umma_bf16_ts(td, tq + 8 * k, dk + (uint64_t)(2 * k), idesc_s, k != 0);
+          umma_bf16_ts(td, tq + 32, make_smem_desc_sw32(ka + K64_BYTES), idesc_s, 1);
+          umma_commit(&s_full[qt]);
+          if (qt == 1) umma_commit(&k_empty[stage]);   // both S of tile t issued: the K slot is free once they retire
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int qt, int t) {   // O_qt += P_qt(t) V(t)
+      auto issue_pv = [&](int qt, int t) {   // O_qt += P_qt(t) V(t), A = P from TMEM (over S_qt's first 64 columns)
         const int stage = t % STAGES;
         if (qt == 0) mbar_wait(&v_full[stage], (uint32_t)((t / STAGES) & 1));
         mbar_wait(&p_full[qt], (uint32_t)(t & 1));
+        istamp(t, 4 * qt + 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP + qt * P_BYTES);
         const uint32_t va = smem_u32(sKV + stage * STAGE_BYTES + K64_BYTES + K16_BYTES);
         const uint32_t td = tmem_base + (qt == 0 ? TMEM_O0 : TMEM_O1);
+        const uint32_t tp = tmem_base + (qt == 0 ? TMEM_S0 : TMEM_S1);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t dp = make_smem_desc_sw128(pa + (kk >> 2) * (BQ * 128)) + (uint64_t)(2 * (kk & 3));
-          const uint64_t dv = make_smem_desc_sw128(va + (kk >> 2) * VT_ATOM_BYTES) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(td, dp, dv, idesc_o, (t > 0 || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t dv = make_smem_desc_sw128(va + (kk >> 2) * VT_ATOM_BYTES) + (uint64_t)(2 * (kk & 3));
+            umma_bf16_ts(td, tp + 8 * kk, dv, idesc_o, (t > 0 || kk != 0) ? 1u : 0u);
+          }
+          if (qt == 1) umma_commit(&v_empty[stage]);
+          if (t + 1 == n_tiles) umma_commit(&o_full[qt]);
         }
-        if (qt == 1) umma_commit(&v_empty[stage]);
-        if (t + 1 < n_tiles)
-          umma_commit(&pv_done[qt]);     // softmax(qt, t+1) may overwrite P_qt / rescale O_qt once this fires
-        else
-          umma_commit(&o_full[qt]);
+        __syncwarp();
       };
-      // Issue order = steady-state order of the events when the two query tiles run in anti-phase:
-      //   P V_0(j), S_0(j+2), P V_1(j), S_1(j+2)   (S runs two tiles ahead: S(j+1) is consumed while P(j) is produced)
-      mbar_wait(q_full, 0);
 #pragma unroll 1
-      for (int t = 0; t < 2 && t < n_tiles; ++t) {
-#pragma unroll 1
-        for (int qt = 0; qt < 2; ++qt) issue_s(qt, t);
+      for (int qt = 0; qt < 2; ++qt) {
+        mbar_wait(&q_ready[qt], 0);
+        issue_s(qt, 0);
       }
 #pragma unroll 1
       for (int j = 0; j < n_tiles; ++j) {
 #pragma unroll 1
         for (int qt = 0; qt < 2; ++qt) {
-          stamp(2, j, 2 * qt);
+          istamp(j, 4 * qt);
           issue_pv(qt, j);
-          stamp(2, j, 2 * qt + 1);
-          if (j + 2 < n_tiles) issue_s(qt, j + 2);
+          istamp(j, 4 * qt + 2);
+          if (j + 1 < n_tiles) issue_s(qt, j + 1);   // in-order pipe: overwrites S/P only after P V(j) has read P
+          istamp(j, 4 * qt + 3);
         }
-        stamp(2, j, 4);
       }
     }
   } else {
@@ -287,10 +301,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
     const int qt = (warp - 4) >> 2;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;          // row inside the tile == TMEM lane
-    const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (qt == 0 ? TMEM_S0 : TMEM_S1);
-    const uint32_t t_o = tmem_base + ((uint32_t)(quarter * 32) << 16) + (qt == 0 ? TMEM_O0 : TMEM_O1);
-    const uint32_t prow = smem_u32(sP + qt * P_BYTES + r * 128);
-    const int rx = r & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_s = lane_base + (qt == 0 ? TMEM_S0 : TMEM_S1);
+    const uint32_t t_o = lane_base + (qt == 0 ? TMEM_O0 : TMEM_O1);
+    const int row = q0 + qt * BQ + r;
+    {
+      // this thread's query row -> TMEM as the A operand of S = Q K^T: bf16 pairs, d 72..79 (and rows beyond T) zero
+      uint32_t qv[48];
+#pragma unroll
+      for (int i = 0; i < 48; ++i) qv[i] = 0u;
+      if (row < p.T) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + (((long)b * p.H + head) * p.T + row) * HD);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const uint4 v = __ldg(src + i);
+          qv[4 * i] = v.x;
+          qv[4 * i + 1] = v.y;
+          qv[4 * i + 2] = v.z;
+          qv[4 * i + 3] = v.w;
+        }
+      }
+      const uint32_t t_q = lane_base + (qt == 0 ? TMEM_Q0 : TMEM_Q1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t part[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[i] = qv[c * 16 + i];
+        tmem_st_32x16(t_q + c * 16, part);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&q_ready[qt]);
+    }
     const uint64_t scale2 = pack2(p.scale_log2e, p.scale_log2e);
     float m_used = -INFINITY;
     uint64_t l2 = pack2(0.f, 0.f);   // running row sum, two partial sums (rescaled together)
@@ -303,8 +345,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, s[c]);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[qt]);   // S lives in registers now: the tensor core may start the next S of this tile
       if (quarter == 0) stamp(qt, j, 2);
       const int kbase = j * BKV;
       if (kbase + BKV > p.T) {
@@ -325,17 +365,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       if (quarter == 0) stamp(qt, j, 3);
       // lazy rescale: keep the stale max unless it grew by more than 8 (p stays below 2^8, exact in fp32 / fine in bf16)
       const bool grow = (m_new - m_used) > 8.0f;   // also true on the first tile (m_used = -inf)
-      bool pv_waited = (j == 0);
       if (__any_sync(0xffffffffu, grow)) {
         const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
         if (grow) m_used = m_new;
         const uint64_t alpha2 = pack2(alpha, alpha);
         l2 = fma2(l2, alpha2, pack2(0.f, 0.f));
         if (j > 0) {
-          // P*V(qt, j-1) must have finished accumulating into O_qt before it is rescaled
-          mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-          pv_waited = true;
+          // O_qt holds P V(0..j-1): complete, because S(j) (observed through s_full) was issued behind P V(j-1)
 #pragma unroll
           for (int c = 0; c < NV / 16; ++c) {
             uint32_t o[16];
@@ -345,7 +381,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x16(t_o + c * 16, o);
           }
-          tmem_st_wait();
         }
       }
       const uint64_t negm2 = pack2(-m_used, -m_used);
@@ -354,9 +389,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
       uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
       if (ORDER) mbar_wait(&order[qt], (uint32_t)((j & 1) ^ (qt == 0 ? 1 : 0)));   // tile 0's first turn is free
       if (quarter == 0) stamp(qt, j, 4);
-      uint32_t pk[64];   // P row as packed bf16 pairs: kept in registers until P*V(j-1) has released the P buffer
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];   // 32 keys of the P row as bf16 pairs -> 16 TMEM columns over S(j), which lives in registers now
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
 #pragma unroll
@@ -382,25 +417,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
               sum_b = add2(sum_b, pack2(e0, e1));
             else
               sum_a = add2(sum_a, pack2(e0, e1));
-            pk[c * 16 + g * 4 + pr] = pack_bf16x2(e0, e1);
+            pk[g * 4 + pr] = pack_bf16x2(e0, e1);
           }
         }
+        tmem_st_32x16(t_s + c * 16, pk);
         if (ORDER > 0 && c == ORDER - 1) mbar_arrive(&order[qt ^ 1]);   // hand the MUFU over
       }
       l2 = add2(l2, add2(sum_a, sum_b));
       if (quarter == 0) stamp(qt, j, 5);
-      if (!pv_waited) {
-        // P*V(qt, j-1) must have finished reading P_qt before it is overwritten
-        mbar_wait(&pv_done[qt], (uint32_t)((j - 1) & 1));
-      }
-#pragma unroll
-      for (int jc = 0; jc < 16; ++jc) {   // 16-byte chunks (8 keys) of the 128-key row, 128B-swizzled K-major
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)((jc >> 3) * (BQ * 128)) +
-                                                                      (uint32_t)(((jc & 7) ^ rx) << 4)),
-                     "r"(pk[jc * 4]), "r"(pk[jc * 4 + 1]), "r"(pk[jc * 4 + 2]), "r"(pk[jc * 4 + 3])
-                     : "memory");
-      }
-      fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
+      tmem_st_wait();        // P (and a rescaled O) are in TMEM
       tc_fence_before();
       mbar_arrive(&p_full[qt]);
       if (quarter == 0) stamp(qt, j, 6);
@@ -411,7 +436,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constant_
     // ---- epilogue: O / l -> bf16 -> out[(b*T + row)][head*72 + d]
     mbar_wait(&o_full[qt], 0);
     tc_fence_after();
-    const int row = q0 + qt * BQ + r;
     const float inv = l > 0.f ? 1.0f / l : 0.f;
     uint32_t o[32];
     bf16* og = p.out + ((long)b * p.T + row) * p.ldo + head * HD;
@@ -459,14 +483,12 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.head_dim == HD, "attention_tc: head_dim %d unsupported (kernel is specialised for %d)", a.head_dim, HD);
   IR_REQUIRE(a.q && a.k && a.vt && a.out && a.B > 0 && a.H > 0 && a.T > 0, "attention_tc: bad arguments");
   IR_REQUIRE(a.Tp % 8 == 0 && a.Tp >= a.T && a.ldo % 8 == 0, "attention_tc: Tp must be a multiple of 8 and >= T");
-  CUtensorMap mq64, mq16, mk64, mk16, mvt;
+  CUtensorMap mk64, mk16, mvt;
   {
     const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)a.T, (uint64_t)a.H, (uint64_t)a.B};
     const uint64_t strides[3] = {(uint64_t)HD * 2, (uint64_t)a.T * HD * 2, (uint64_t)a.H * a.T * HD * 2};
-    const uint32_t box64[4] = {64, BQ, 1, 1};
-    const uint32_t box16[4] = {16, BQ, 1, 1};
-    IR_TRY(make_tensor_map(&mq64, a.q, 4, dims, strides, box64, 128));
-    IR_TRY(make_tensor_map(&mq16, a.q, 4, dims, strides, box16, 32));
+    const uint32_t box64[4] = {64, BKV, 1, 1};
+    const uint32_t box16[4] = {16, BKV, 1, 1};
     IR_TRY(make_tensor_map(&mk64, a.k, 4, dims, strides, box64, 128));
     IR_TRY(make_tensor_map(&mk16, a.k, 4, dims, strides, box16, 32));
   }
@@ -477,6 +499,7 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
     IR_TRY(make_tensor_map(&mvt, a.vt, 4, dims, strides, box, 128));
   }
   AttnTcDev p;
+  p.q = a.q;
   p.out = a.out;
   p.ldo = a.ldo;
   p.T = a.T;
@@ -500,7 +523,7 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
     }
     const bool prof = prof_enabled();
     if (prof) prof_before(stream);
-    IR_CUDA_CHECK(launch_pdl(kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mq64, mq16, mk64, mk16, mvt, p));
+    IR_CUDA_CHECK(launch_pdl(kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mk64, mk16, mvt, p));
     if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD);
     return IR_OK;
   };

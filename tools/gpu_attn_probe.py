@@ -61,11 +61,11 @@ def trace(B=1, T=4096):
     nt = (T + 127) // 128
     t0 = int(t[0, 0, 0])
     names = {0: ["start", "s_full", "S in regs", "max done", "pv_done", "exp done", "p_full arrive"],
-             2: ["PV0 wait", "PV0 issued", "S0 issued", "PV1 issued", "S1 issued"]}
+             2: ["t0 start", "p_full0", "PV0 issued", "S0 issued", "t1 start", "p_full1", "PV1 issued", "S1 issued"]}
     for role in range(3):
         nm = names[0] if role < 2 else names[2]
         print(f"--- role {role} ({'softmax' if role < 2 else 'mma'} tile {role & 1}); columns = {nm}; clocks relative to CTA start, then per-slot deltas")
-        for j in list(range(0, 6)) + list(range(nt - 3, nt)):
+        for j in list(range(0, 3)) + list(range(10, 16)) + list(range(nt - 2, nt)):
             row = [int(v) for v in t[role, j, :len(nm)]]
             rel = [v - t0 if v else 0 for v in row]
             d = [rel[i] - rel[i - 1] if (i and row[i] and row[i - 1]) else 0 for i in range(len(rel))]
