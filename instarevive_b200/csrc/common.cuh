@@ -112,6 +112,13 @@ IR_DEVINL float lds_f1(uint32_t saddr) {
   return v;
 }
 
+// One lane of a converged warp (elect.sync); used to issue uniform-datapath instructions from convergent code.
+IR_DEVINL bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor is still
 // draining; it must execute pdl_wait() before its first global-memory access that depends on (or could overwrite data

@@ -99,7 +99,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so the producer / issuer branches are convergent and the
+  // uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) are emitted directly; under a divergent `lane == 0` the
+  // compiler wraps every one of them in an elect-one loop (~80 cycles per MMA: more than a 128 x 128 x 16 MMA takes)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -140,8 +143,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (convergent warp, one lane issues)
+    const bool leader = elect_one_sync();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < p.num_tiles; tile += unit_stride) {
@@ -157,6 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_row0 = n_blk * BN + (int)cta_rank * Cfg::B_ROWS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) {
           if (CG == 2) {
             if (cta_rank == 0)
               mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
@@ -192,6 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kb * BK, n_row0, b);
             }
           }
+          }   // leader
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -200,8 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (convergent warp, one lane issues)
+    if (cta_rank == 0) {
+      const bool leader = elect_one_sync();
       constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -217,14 +225,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           constexpr int TAPS = CONV ? 3 : 1;
           if (CG == 1 && p.dbg_nomma) {
-            mbar_arrive(&empty_bar[stage]);
-            if (kb == p.k_blocks - 1) mbar_arrive(&tfull_bar[buf]);
+            if (leader) {
+              mbar_arrive(&empty_bar[stage]);
+              if (kb == p.k_blocks - 1) mbar_arrive(&tfull_bar[buf]);
+            }
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
             continue;
           }
+          if (leader) {
 #pragma unroll
           for (int ky = 0; ky < TAPS; ++ky) {
             // conv: tap ky reads rows [16*ky, 16*ky + 128) of the halo box (+2048 B keeps the 1024 B swizzle phase)
@@ -246,6 +258,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             if (kb == p.k_blocks - 1) umma_commit(&tfull_bar[buf]);
           }
+          }   // leader
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
