@@ -269,7 +269,7 @@ def run_cuda(args):
     traffic = None
     try:
         import csv
-        with open(ROOT / "profiles" / "r01_ncu_full_gemm_attn_final_summary.csv") as f:
+        with open(ROOT / "profiles" / "r01_ncu_full_step_summary.csv") as f:
             rows = list(csv.reader(f))
         hdr, units = rows[0], rows[1]
         ir_, iw_, in_ = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
@@ -278,7 +278,7 @@ def run_cuda(args):
                 for r in rows[2:] if "gemm_tc_kernel" in r[in_]]
         if vals:
             traffic = {"dram_bytes_per_launch_avg": sum(vals) / len(vals), "launches_sampled": len(vals),
-                       "source": "profiles/r01_ncu_full_gemm_attn_final_summary.csv (DiT linear launches of one 1024x1024 step)"}
+                       "source": "profiles/r01_ncu_full_step_summary.csv (DiT linear launches of one 1024x1024 step)"}
     except Exception:
         traffic = None
     roofline = None

@@ -50,6 +50,7 @@ struct GemmCfg {
 struct GemmDev {
   int M, N, K;
   int k_blocks;    // K-blocks per tile
+  int raster_n;    // tile order: 1 = N blocks fastest, 0 = M blocks fastest
   int m_blocks;    // 128-row M tiles per batch entry (per image for conv)
   int m_units;     // scheduling units per batch entry: m_blocks (CG 1) or ceil(m_blocks / 2) pairs (CG 2)
   int n_blocks;
@@ -149,8 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < p.num_tiles; tile += unit_stride) {
-        const int n_blk = tile / mb_total;
-        const int mb = tile - n_blk * mb_total;
+        // raster_n: consecutive tiles walk the N blocks of one M block (A streamed from HBM once, W stays in L2)
+        const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+        const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
         const int b = mb / p.m_units;
         const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;   // may exceed m_blocks (odd tail): all OOB -> zeros
         int ty = 0, tx = 0;
@@ -284,8 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool gn_on = (EPI == EPI_BF16) && p.gn_partial != nullptr;
     int it = 0;
     for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
-      const int n_blk = tile / mb_total;
-      const int mb = tile - n_blk * mb_total;
+      const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+      const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
       const int b = mb / p.m_units;
       const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
       const int buf = it & 1;
@@ -716,10 +718,12 @@ struct TileCfg {
   int cg, bn;
 };
 
-// Tile configuration: CTA-pair tiles (cta_group::2, 256 x BN) or single-CTA tiles (128 x BN). Relative time per
-// scheduling unit calibrated on B200 (narrow tiles are bound by L2 -> shared-memory operand traffic per FLOP);
-// +15 % of a unit for the exposed last epilogue; waves = units / (SMs / CG).
-static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forced, bool conv) {
+// Tile configuration: CTA-pair tiles (cta_group::2, 256 x BN) or single-CTA tiles (128 x BN).
+// cost = waves * k_steps * (time per K-block step of one scheduling unit) + the exposed epilogue of the last tile;
+// waves = units / (SMs / CG). Step times measured on B200 with the convergent issue path (tools/gpu_kernel_check.py
+// perf: 8192^3, M4096 x {N4608 K1152, N1152 K4608, N1152 K1152}): per FLOP the 128-wide pair tile costs about what the
+// 256-wide one does, so it wins whenever it quantises better (N = 1152 = 9 x 128).
+static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int k_steps, int forced, bool conv) {
   static int env_cg = -1, env_bn = 0;
   if (env_cg < 0) {
     const char* e = getenv("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
@@ -732,9 +736,8 @@ static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forc
     return TileCfg{env_cg, env_bn};
   const int sms = num_sms();
   const TileCfg cands[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
-  // measured time per K-block step (us, B200, L2-resident operands): the mainloop is bound by L2 -> SM operand
-  // traffic, so wide CTA-pair tiles (128 FLOP/B) win whenever the wave quantisation allows them
-  const double unit_cost[5] = {0.50, 0.48, 0.53, 0.52, 0.41};
+  const double unit_cost[5] = {0.415, 0.24, 0.50, 0.285, 0.245};   // us per K-block step
+  const double epi_cost[5] = {2.0, 1.0, 2.0, 1.0, 0.6};            // us, last tile's epilogue (not overlapped)
   TileCfg best = cands[3];
   double best_cost = 1e30;
   for (int i = 0; i < 5; ++i) {
@@ -744,7 +747,7 @@ static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int forc
     const long units = (cg == 2 ? m_pairs_total : m_blocks_total) * ((N + bn - 1) / bn);
     const long slots = sms / cg;
     const long waves = (units + slots - 1) / slots;
-    const double cost = ((double)waves + 0.15) * unit_cost[i];
+    const double cost = (double)waves * k_steps * unit_cost[i] + epi_cost[i];
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
       best = cands[i];
@@ -850,12 +853,16 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
   const long m_pairs = (p.m_blocks + 1) / 2;
-  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.force_bn, a.conv != 0);
+  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.conv ? 3 * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
   if (a.conv && tc.cg == 1 && tc.bn == 256) tc.bn = 128;
   const int bn = tc.bn;
   p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;
   p.n_blocks = (a.N + bn - 1) / bn;
   p.num_tiles = (int)((long)p.m_units * p.batch * p.n_blocks);
+  // the operand that is re-read by the slower-moving tile index should be the one that fits in L2: walk N fastest when
+  // the activations outweigh the weights (token GEMMs at M > N: M25600 N1152 K4608 243 -> 211 us), M fastest otherwise
+  // (convs measured neutral-to-worse with N fastest, so they keep the M-fastest order)
+  p.raster_n = (!a.conv && a.batch == 1 && a.M > a.N) ? 1 : 0;
   {
     const int wb = a.conv ? 1 : a.batch;
     const uint64_t dims[3] = {(uint64_t)a.K, (uint64_t)a.N, (uint64_t)wb};

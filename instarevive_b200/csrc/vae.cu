@@ -187,13 +187,18 @@ __global__ void __launch_bounds__(256) gn_finalize_fused_kernel(const float* __r
 }
 
 // Stage 3: y = act((x - mean) * rstd * gamma + beta) -> bf16; act = SiLU (x * sigmoid(x), model.py:43-45) or none.
+// grid = (blocks per image, images): the image index comes from blockIdx.y and a thread keeps its channel slot (the
+// vectors-per-pixel count divides the block size), so the per-vector work has no integer division and the per-thread
+// affine map  y = x * a + b  (a = rstd * gamma, b = beta - mean * a) is computed once. The grid is sized to the
+// resident block count (3 per SM) and every thread keeps 8 independent 16 B loads in flight.
 template <bool SILU>
 __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                        const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, long total_vec, int P, int C) {
+                                                       const float* __restrict__ beta, int vec_per_img, int C) {
   const int tpp = C / 8;   // 16-byte vectors per pixel; divides the block size, so a thread keeps its channel slot
   const int cpg = C / 32;
   const int c0 = (threadIdx.x % tpp) * 8;
+  const int n = blockIdx.y;
   pdl_wait();
   pdl_launch();
   const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
@@ -201,38 +206,44 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const bf16* __restrict
   const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
   const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   const int g_lo = c0 / cpg, g_hi = (c0 + 4) / cpg;
-  const long stride = (long)gridDim.x * blockDim.x;
-  auto one = [&](long i, const uint4& u) {
-    const int n = (int)((i / tpp) / P);
-    const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_lo) * 2);
-    const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_hi) * 2);
+  const float2 st_lo = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_lo) * 2);
+  const float2 st_hi = *reinterpret_cast<const float2*>(stats + ((long)n * 32 + g_hi) * 2);
+  float ka[8], kb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 st = k < 4 ? st_lo : st_hi;
+    ka[k] = st.y * gm[k];
+    kb[k] = bt[k] - st.x * ka[k];
+  }
+  const bf16* xi = x + (long)n * vec_per_img * 8;
+  bf16* yi = y + (long)n * vec_per_img * 8;
+  const int stride = gridDim.x * blockDim.x;
+  auto one = [&](int i, const uint4& u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 st = k < 2 ? st_lo : st_hi;
       const float2 a = unpack_bf16x2(w[k]);
-      float t0 = (a.x - st.x) * st.y * gm[2 * k] + bt[2 * k];
-      float t1 = (a.y - st.x) * st.y * gm[2 * k + 1] + bt[2 * k + 1];
+      float t0 = fmaf(a.x, ka[2 * k], kb[2 * k]);
+      float t1 = fmaf(a.y, ka[2 * k + 1], kb[2 * k + 1]);
       if (SILU) {
         t0 = silu_fast(t0);
         t1 = silu_fast(t1);
       }
       o[k] = pack_bf16x2(t0, t1);
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(yi + (long)i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   };
-  // 8 independent 16 B loads in flight per thread (HBM latency x bandwidth needs ~64 KB in flight per SM)
   constexpr int U = 8;
-  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  for (; i + (U - 1) * stride < total_vec; i += U * stride) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < vec_per_img; i += U * stride) {
     uint4 u[U];
 #pragma unroll
-    for (int k = 0; k < U; ++k) u[k] = *reinterpret_cast<const uint4*>(x + (i + k * stride) * 8);
+    for (int k = 0; k < U; ++k) u[k] = *reinterpret_cast<const uint4*>(xi + (long)(i + k * stride) * 8);
 #pragma unroll
     for (int k = 0; k < U; ++k) one(i + k * stride, u[k]);
   }
-  for (; i < total_vec; i += stride) one(i, *reinterpret_cast<const uint4*>(x + i * 8));
+  for (; i < vec_per_img; i += stride) one(i, *reinterpret_cast<const uint4*>(xi + (long)i * 8));
 }
 
 // ------------------------------------------------------------------------------------------------ upsample
@@ -606,17 +617,22 @@ static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
                              1.0 / ((double)P * (C / 32)), 1e-6f));
     count_launch(2);
   }
-  const long total_vec = (long)c.B * P * C / 8;
-  int grid = div_up_l(total_vec, 256);
-  if (grid > 148 * 16) grid = 148 * 16;
+  const long vec_per_img_l = (long)P * C / 8;
+  IR_REQUIRE(vec_per_img_l < (1L << 30) && 256 % (C / 8) == 0, "group_norm: image too large / channel count unsupported");
+  const int vec_per_img = (int)vec_per_img_l;
+  // resident blocks (3 per SM) split over the images of the batch; never more blocks than 8-vector work items
+  int gx = (device_num_sms() * 3 + c.B - 1) / c.B;
+  const int need = div_up_l(vec_per_img, 256 * 8);
+  if (gx > need) gx = need;
+  if (gx < 1) gx = 1;
   const float* gamma = vp<float>(c.v, name + ".weight");
   const float* beta = vp<float>(c.v, name + ".bias");
   if (silu_act)
-    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<true>, dim3(grid), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
-                             total_vec, P, C));
+    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<true>, dim3(gx, c.B), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
+                             vec_per_img, C));
   else
-    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<false>, dim3(grid), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
-                             total_vec, P, C));
+    IR_CUDA_CHECK(launch_pdl(gn_apply_kernel<false>, dim3(gx, c.B), dim3(256), 0, c.s, x, y, (const float*)c.w.stats, gamma, beta,
+                             vec_per_img, C));
   count_launch(3);
   return IR_OK;
 }

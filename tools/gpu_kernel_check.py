@@ -258,6 +258,18 @@ def main():
             for bn in (128, 256, 2128, 2256):
                 if bn % 1000 <= Co:
                     conv_perf(1, H, H, C, Co, bn)
+    if "calib" in which:
+        # tile-configuration calibration sweep for pick_cfg (gemm.cu): the shapes of the 1024^2 and tiled-2048^2 workloads
+        for M in (4096, 9216, 25600):
+            for (N, K) in [(1152, 1152), (3456, 1152), (4608, 1152), (1152, 4608)]:
+                for bn in (128, 256, 2128, 2256):
+                    gemm_perf(M, N, K, bn)
+        for (n, H, C, Co) in [(1, 128, 512, 512), (1, 256, 512, 512), (1, 256, 512, 256), (1, 256, 256, 256),
+                              (1, 512, 256, 256), (1, 512, 256, 128), (1, 512, 128, 128), (1, 1024, 128, 128),
+                              (4, 64, 512, 512), (4, 128, 512, 512), (4, 256, 256, 256), (4, 512, 128, 128)]:
+            for bn in (128, 2128, 2256):
+                if bn % 1000 <= Co:
+                    conv_perf(n, H, H, C, Co, bn)
     print("ALL OK" if ok_all else "SOME FAILED", flush=True)
     return 0 if ok_all else 1
 
