@@ -267,6 +267,7 @@ def run_cuda(args):
     peak_tf, peak_hbm, peak_src = _peaks()
     # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture (profiles/)
     traffic = None
+    traffic_src = None
     try:
         import csv
         with open(ROOT / "profiles" / "r01_ncu_full_step_summary.csv") as f:
@@ -277,8 +278,9 @@ def run_cuda(args):
         vals = [float(r[ir_]) * scale.get(units[ir_], 1.0) + float(r[iw_]) * scale.get(units[iw_], 1.0)
                 for r in rows[2:] if "gemm_tc_kernel" in r[in_]]
         if vals:
-            traffic = {"dram_bytes_per_launch_avg": sum(vals) / len(vals), "launches_sampled": len(vals),
-                       "source": "profiles/r01_ncu_full_step_summary.csv (DiT linear launches of one 1024x1024 step)"}
+            traffic = sum(vals) / len(vals)   # bytes per launch, averaged over the captured launches
+            traffic_src = (f"profiles/r01_ncu_full_step_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of "
+                           f"{len(vals)} gemm_tc_kernel launches of one 1024x1024 step (ncu --set full, L2 flushed per launch)")
     except Exception:
         traffic = None
     roofline = None
@@ -289,7 +291,7 @@ def run_cuda(args):
         g_n = prof["gemm"][2] + prof["conv"][2]
         ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "launches": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
                     "share_of_step": g_ms / args.steps / (total_ms / args.steps)}
         kernels = {k: {"ms_per_step": v[0] / args.steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12) if v[0] > 0 else None,

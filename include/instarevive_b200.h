@@ -105,6 +105,7 @@ typedef struct ir_vae_config {
   int out_ch;         /* 3 */
   int num_res_blocks; /* 2 */
   int ch_mult[4];     /* 1,2,4,4 */
+  int with_encoder;   /* nonzero: the handle also holds encoder.* and quant_conv.* and can run ir_vae_encode */
 } ir_vae_config;
 
 int ir_vae_create(const ir_vae_config* cfg, ir_vae** out);
@@ -118,6 +119,15 @@ size_t ir_vae_workspace_bytes(const ir_vae* h, int B, int h_lat, int w_lat);
  * in_scale = 1/scaling_factor and out = x/2 + 0.5 reproduce test_scripts/inference.py:116-117,140-142. */
 int ir_vae_decode(ir_vae* h, const float* z, float* out, int B, int h_lat, int w_lat, float in_scale, float out_scale,
                   float out_shift, void* workspace, size_t workspace_bytes, void* stream);
+
+/* VAE encoder: moments (B, 8, H/8, W/8) fp32 = quant_conv(Encoder(x)), x: (B,3,H,W) fp32 in [-1,1]
+ * (AutoencoderKL.encode, ldm/models/autoencoder.py:82-86; Encoder.forward, ldm/modules/diffusionmodules/model.py:521-546;
+ * Downsample, model.py:70-89). Channels [0,4) are the mean = DiagonalGaussianDistribution.mode()
+ * (ldm/modules/distributions/distributions.py:24-62), channels [4,8) the log-variance. Parameter names:
+ * encoder.*, quant_conv.{weight,bias}. H and W must be multiples of 16. */
+size_t ir_vae_encode_workspace_bytes(const ir_vae* h, int B, int H, int W);
+int ir_vae_encode(ir_vae* h, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                  void* stream);
 
 /* ------------------------------------------------------------------ tile scheduler / pixel post-processing ---- */
 /* coords: device int32 [ntiles][2] = (hi, wi) window origins from _sliding_windows (test_scripts/inference.py:40-53),

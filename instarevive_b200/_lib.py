@@ -22,7 +22,8 @@ class DitConfig(C.Structure):
 
 
 class VaeConfig(C.Structure):
-    _fields_ = [("ch", _i), ("z_channels", _i), ("out_ch", _i), ("num_res_blocks", _i), ("ch_mult", _i * 4)]
+    _fields_ = [("ch", _i), ("z_channels", _i), ("out_ch", _i), ("num_res_blocks", _i), ("ch_mult", _i * 4),
+                ("with_encoder", _i)]
 
 
 # name -> (restype, argtypes); every symbol of include/instarevive_b200.h must appear here
@@ -56,6 +57,8 @@ PROTOTYPES = {
     "ir_vae_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
     "ir_vae_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "ir_vae_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
+    "ir_vae_encode_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "ir_vae_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "ir_tile_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ir_tile_blend": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ir_wavelet_workspace_bytes": (_sz, [_i, _i, _i, _i]),

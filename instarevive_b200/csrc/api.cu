@@ -216,6 +216,7 @@ int ir_vae_create(const ir_vae_config* cfg, ir_vae** out) {
   c.out_ch = cfg->out_ch;
   c.num_res_blocks = cfg->num_res_blocks;
   for (int i = 0; i < 4; ++i) c.ch_mult[i] = cfg->ch_mult[i];
+  c.with_encoder = cfg->with_encoder;
   Vae* v = nullptr;
   int st = vae_create(c, &v);
   if (st != IR_OK) return st;
@@ -265,6 +266,19 @@ int ir_vae_decode(ir_vae* h, const float* z, float* out, int B, int h_lat, int w
   }
   return vae_decode(h->v, z, out, B, h_lat, w_lat, in_scale, out_scale, out_shift, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+
+size_t ir_vae_encode_workspace_bytes(const ir_vae* h, int B, int H, int W) {
+  return h ? vae_encode_workspace_bytes(h->v, B, H, W) : 0;
+}
+
+int ir_vae_encode(ir_vae* h, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (!h) {
+    set_last_error("ir_vae_encode: null handle");
+    return IR_ERR_INVALID;
+  }
+  return vae_encode(h->v, x, moments, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ir_tile_gather(const float* src, float* dst, const int32_t* coords, int ntiles, int N, int C, int H, int W, int th,

@@ -511,10 +511,17 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
     return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();
   auto launch = [&](auto kernel) -> int {
-    static bool configured = false;   // one static per kernel instantiation (the lambda body is instantiated per type)
-    if (!configured) {
+    // every instantiation has the same function-pointer type, so the opt-in shared-memory size is tracked per pointer
+    static const void* configured[16] = {};
+    bool done = false;
+    int free_slot = -1;
+    for (int i = 0; i < 16; ++i) {
+      if (configured[i] == (const void*)kernel) done = true;
+      if (!configured[i] && free_slot < 0) free_slot = i;
+    }
+    if (!done) {
       IR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      configured = true;
+      if (free_slot >= 0) configured[free_slot] = (const void*)kernel;
     }
     const bool prof = prof_enabled();
     if (prof) prof_before(stream);

@@ -18,7 +18,8 @@ static inline int div_up_l(long a, long b) { return (int)((a + b - 1) / b); }
 // post_quant_conv (1x1, zc->zc) folded into conv_in (3x3, zc->Cout, pad 1): the zero padding applies to the
 // post_quant output, so out-of-image taps contribute nothing. z: (B, zc, H, W) fp32, scaled by in_scale first
 // (the caller's `latents / scaling_factor`, test_scripts/inference.py:116,141). out: NHWC bf16.
-template <int ZC>
+// PQ = false: plain 3x3 conv of an NCHW fp32 image (Encoder.conv_in, model.py:456-460).
+template <int ZC, bool PQ = true>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ z, const float* __restrict__ pq_w,
                                                       const float* __restrict__ pq_b, const float* __restrict__ w_t,
                                                       const float* __restrict__ bias, bf16* __restrict__ out, int B,
@@ -45,10 +46,14 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     for (int c = 0; c < ZC; ++c) zin[c] = z[(((long)b * ZC + c) * H + yy) * W + xx] * in_scale;
 #pragma unroll
     for (int o = 0; o < ZC; ++o) {
-      float v = pq_b[o];
+      if (PQ) {
+        float v = pq_b[o];
 #pragma unroll
-      for (int c = 0; c < ZC; ++c) v += pq_w[o * ZC + c] * zin[c];
-      zq[o] = v;
+        for (int c = 0; c < ZC; ++c) v += pq_w[o * ZC + c] * zin[c];
+        zq[o] = v;
+      } else {
+        zq[o] = zin[o];
+      }
     }
 #pragma unroll
     for (int c = 0; c < ZC; ++c) {
@@ -387,6 +392,54 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ encoder helpers
+// Downsample.forward (model.py:82-89): F.pad(x, (0,1,0,1)) then a 3x3 stride-2 conv without padding. The strided
+// gather is materialised as the K-major A operand of a plain GEMM: A[(b,oy,ox)][(ky*3+kx)*C + c] = x[b][2oy+ky][2ox+kx][c]
+// (zero beyond the right / bottom edge), which is exactly the tap-major K layout of the packed conv weights.
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ a, int H, int W, int C,
+                                                        int Ho, int Wo, long total_vec) {
+  const int tpp = C / 8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total_vec; i += stride) {
+    const int cv = (int)(i % tpp);
+    long r = i / tpp;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const long b = r / Ho;
+    const int yy = 2 * oy + tap / 3, xx = 2 * ox + tap % 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy < H && xx < W) v = *reinterpret_cast<const uint4*>(x + (((b * H + yy) * W + xx) * (long)C) + cv * 8);
+    *reinterpret_cast<uint4*>(a + i * 8) = v;
+  }
+}
+
+// quant_conv (1x1, 2z -> 2z, autoencoder.py:84) on the fp32 NHWC output of Encoder.conv_out, written as the NCHW
+// fp32 `moments` tensor (mean = channels [0, z), logvar = channels [z, 2z); distributions.py:27).
+template <int CZ>
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ h, const float* __restrict__ qw,
+                                                      const float* __restrict__ qb, float* __restrict__ out, long P_total,
+                                                      int P) {
+  const long pix = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (pix >= P_total) return;
+  float in[CZ];
+#pragma unroll
+  for (int c = 0; c < CZ; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(h + pix * CZ + c);
+    in[c] = v.x; in[c + 1] = v.y; in[c + 2] = v.z; in[c + 3] = v.w;
+  }
+  const long b = pix / P, p = pix % P;
+#pragma unroll
+  for (int o = 0; o < CZ; ++o) {
+    float v = qb[o];
+#pragma unroll
+    for (int c = 0; c < CZ; ++c) v += qw[o * CZ + c] * in[c];
+    out[(b * CZ + o) * P + p] = v;
+  }
+}
+
 // ================================================================================================ handle
 static long align64(long v) { return (v + 63) / 64 * 64; }
 
@@ -455,6 +508,34 @@ int vae_create(const VaeConfig& cfg, Vae** out) {
   }
   vae_add_norm(v, d + ".norm_out", block_in);
   vae_add_conv(v, d + ".conv_out", cfg.out_ch, block_in, 3, VP_CONVOUT_F32);
+  if (cfg.with_encoder) {
+    // Encoder (model.py:440-546) + quant_conv (autoencoder.py:84), reference key names
+    const std::string e = "encoder";
+    v->first_encoder_param = (int)v->params.size();
+    vae_add_conv(v, e + ".conv_in", cfg.ch, 3, 3, VP_CONVIN_F32);
+    int cin = cfg.ch;
+    for (int lvl = 0; lvl < 4; ++lvl) {
+      const int cout = cfg.ch * cfg.ch_mult[lvl];
+      for (int b = 0; b < cfg.num_res_blocks; ++b) {
+        vae_add_res(v, e + ".down." + std::to_string(lvl) + ".block." + std::to_string(b), cin, cout);
+        cin = cout;
+      }
+      if (lvl != 3) vae_add_conv(v, e + ".down." + std::to_string(lvl) + ".downsample.conv", cin, cin, 3);
+    }
+    vae_add_res(v, e + ".mid.block_1", cin, cin);
+    vae_add_norm(v, e + ".mid.attn_1.norm", cin);
+    vae_add(v, e + ".mid.attn_1.q.weight", VP_CONV_BF16, (long)cin * cin, cin, cin, 1);
+    vae_add(v, e + ".mid.attn_1.k.weight", VP_CONV_BF16, (long)cin * cin, cin, cin, 1);
+    vae_add(v, e + ".mid.attn_1.v.weight", VP_CONV_BF16, (long)cin * cin, cin, cin, 1);
+    vae_add(v, e + ".mid.attn_1.q.bias", VP_F32, cin, cin, 1, 1);
+    vae_add(v, e + ".mid.attn_1.k.bias", VP_F32, cin, cin, 1, 1);
+    vae_add(v, e + ".mid.attn_1.v.bias", VP_F32, cin, cin, 1, 1);
+    vae_add_conv(v, e + ".mid.attn_1.proj_out", cin, cin, 1);
+    vae_add_res(v, e + ".mid.block_2", cin, cin);
+    vae_add_norm(v, e + ".norm_out", cin);
+    vae_add_conv(v, e + ".conv_out", 2 * cfg.z_channels, cin, 3);
+    vae_add_conv(v, "quant_conv", 2 * cfg.z_channels, 2 * cfg.z_channels, 1, VP_F32);
+  }
   if (cudaMalloc(&v->wb, (size_t)v->wb_elems * sizeof(bf16)) != cudaSuccess ||
       cudaMalloc(&v->wf, (size_t)v->wf_elems * sizeof(float)) != cudaSuccess) {
     set_last_error("vae_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -536,6 +617,8 @@ struct VaeWs {
   bf16 *qkv, *vt, *pm;
   float *scores, *partial, *stats;
   long partial_elems;
+  bf16* im2col = nullptr;   // encoder only: A operand of the stride-2 downsample convs
+  float* f32tmp = nullptr;  // encoder only: fp32 NHWC output of conv_out
 };
 
 static const int GN_MAX_CHUNKS = 2048;
@@ -774,7 +857,8 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
                float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   IR_REQUIRE(z && out && B > 0 && h > 0 && w > 0, "vae_decode: bad arguments");
   IR_REQUIRE(h % 2 == 0 && w % 2 == 0, "vae_decode: latent size must be even");
-  for (const VaeParam& p : v->params) IR_REQUIRE(p.loaded, "vae_decode: parameter '%s' was never loaded", p.name.c_str());
+  for (int i = 0; i < (int)v->params.size() && (v->first_encoder_param < 0 || i < v->first_encoder_param); ++i)
+    IR_REQUIRE(v->params[i].loaded, "vae_decode: parameter '%s' was never loaded", v->params[i].name.c_str());
   const size_t need = vae_workspace_bytes(v, B, h, w);
   if (!workspace || workspace_bytes < need) {
     set_last_error("vae_decode: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -841,6 +925,167 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
     IR_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
+  return IR_OK;
+}
+
+// ================================================================================================ encode
+static size_t vae_enc_carve(const Vae* v, VaeWs& w, void* base, int B, int H, int W) {
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    off = (off + 255) & ~size_t(255);
+    void* p = b ? b + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  // largest activation: level 0 (ch channels at full resolution); deeper levels halve the pixels per channel doubling
+  long cmax = 0, imax = 0;
+  {
+    long Hc = H, Wc = W, C = v->cfg.ch;
+    for (int lvl = 0; lvl < 4; ++lvl) {
+      const long Cout = (long)v->cfg.ch * v->cfg.ch_mult[lvl];
+      cmax = std::max(cmax, (long)B * Hc * Wc * std::max(C, Cout));
+      C = Cout;
+      if (lvl != 3) {
+        Hc /= 2;
+        Wc /= 2;
+        imax = std::max(imax, (long)B * Hc * Wc * 9 * C);
+      }
+    }
+  }
+  for (int i = 0; i < 4; ++i) w.buf[i] = reinterpret_cast<bf16*>(take((size_t)cmax * sizeof(bf16)));
+  w.im2col = reinterpret_cast<bf16*>(take((size_t)imax * sizeof(bf16)));
+  const long h = H / 8, wd = W / 8;
+  const long P = h * wd, C = (long)v->cfg.ch * v->cfg.ch_mult[3];
+  w.qkv = reinterpret_cast<bf16*>(take((size_t)B * P * 3 * C * sizeof(bf16)));
+  w.vt = reinterpret_cast<bf16*>(take((size_t)P * C * sizeof(bf16)));
+  w.pm = reinterpret_cast<bf16*>(take((size_t)P * P * sizeof(bf16)));
+  w.scores = reinterpret_cast<float*>(take((size_t)P * P * sizeof(float)));
+  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(H, W)) * 64;
+  w.partial = reinterpret_cast<float*>(take((size_t)w.partial_elems * sizeof(float)));
+  w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
+  w.f32tmp = reinterpret_cast<float*>(take((size_t)B * P * 2 * v->cfg.z_channels * sizeof(float)));
+  return (off + 255) & ~size_t(255);
+}
+
+size_t vae_encode_workspace_bytes(const Vae* v, int B, int H, int W) {
+  VaeWs ws;
+  return vae_enc_carve(v, ws, nullptr, B, H, W);
+}
+
+// Downsample.forward: im2col (stride 2, zero pad right / bottom) + GEMM against the tap-major packed 3x3 weights.
+// The output feeds the next level's first norm1, so its GroupNorm statistics come out of the GEMM epilogue.
+static int downsample(VCtx& c, const std::string& name, const bf16* x, bf16* y, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long M = (long)c.B * Ho * Wo;
+  const long total_vec = M * 9 * (C / 8);
+  int grid = div_up_l(total_vec, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  im2col_s2_kernel<<<grid, 256, 0, c.s>>>(x, c.w.im2col, H, W, C, Ho, Wo, total_vec);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  GemmArgs g;
+  g.A = c.w.im2col;
+  g.lda = 9L * C;
+  g.W = vp<bf16>(c.v, name + ".weight");
+  g.ldw = 9L * C;
+  g.M = (int)M;
+  g.N = C;
+  g.K = 9 * C;
+  g.epi = EPI_BF16;
+  g.bias = vp<float>(c.v, name + ".bias");
+  g.out_bf16 = y;
+  g.ldo_b = C;
+  const int stats_P = Ho * Wo;
+  const int nslots = stats_P / 128;   // one partial per 128-row M block (GEMM path)
+  const bool fuse = fused_stats_ok(C) && stats_P % 128 == 0 && (long)c.B * nslots * 64 <= c.w.partial_elems;
+  if (fuse) {
+    g.gn_partial = c.w.partial;
+    g.gn_cpg = C / 32;
+    g.gn_rows_per_img = stats_P;
+  }
+  IR_TRY(gemm_launch(g, c.s));
+  if (fuse) IR_TRY(finish_fused_stats(c, stats_P, C, nslots));
+  return IR_OK;
+}
+
+// AutoencoderKL.encode up to the moments (autoencoder.py:82-86): Encoder.forward (model.py:521-546) + quant_conv.
+// x: (B,3,H,W) fp32 in [-1,1]; moments: (B, 2z, H/8, W/8) fp32 (mean | logvar).
+int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+               cudaStream_t s) {
+  IR_REQUIRE(v->cfg.with_encoder && v->first_encoder_param >= 0, "vae_encode: handle was created without the encoder");
+  IR_REQUIRE(x && moments && B > 0 && H > 0 && W > 0, "vae_encode: bad arguments");
+  IR_REQUIRE(H % 16 == 0 && W % 16 == 0, "vae_encode: image size must be a multiple of 16 (got %dx%d)", H, W);
+  for (int i = v->first_encoder_param; i < (int)v->params.size(); ++i)
+    IR_REQUIRE(v->params[i].loaded, "vae_encode: parameter '%s' was never loaded", v->params[i].name.c_str());
+  const size_t need = vae_encode_workspace_bytes(v, B, H, W);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("vae_encode: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  VCtx c;
+  c.v = v;
+  c.B = B;
+  c.s = s;
+  vae_enc_carve(v, c.w, workspace, B, H, W);
+  const std::string e = "encoder";
+  const VaeConfig& cfg = v->cfg;
+  int C = cfg.ch;
+  int cur = 0;
+  {
+    const long threads = (long)B * H * W * (C / 8);
+    conv_in_kernel<3, false><<<div_up_l(threads, 256), 256, 0, s>>>(x, nullptr, nullptr, vp<float>(v, e + ".conv_in.weight"),
+                                                                     vp<float>(v, e + ".conv_in.bias"), c.w.buf[cur], B, H,
+                                                                     W, C, 1.0f);
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    const int Cout = cfg.ch * cfg.ch_mult[lvl];
+    for (int b = 0; b < cfg.num_res_blocks; ++b) {
+      // the last block of levels 0..2 feeds the (norm-free) downsample conv; everything else feeds a GroupNorm
+      const bool feeds_norm = (b + 1 < cfg.num_res_blocks) || lvl == 3;
+      IR_TRY(res_block(c, e + ".down." + std::to_string(lvl) + ".block." + std::to_string(b), cur, H, W, C, Cout, feeds_norm));
+      C = Cout;
+    }
+    if (lvl != 3) {
+      IR_TRY(downsample(c, e + ".down." + std::to_string(lvl) + ".downsample.conv", c.w.buf[cur], c.w.buf[(cur + 1) & 3], H, W, C));
+      cur = (cur + 1) & 3;
+      H /= 2;
+      W /= 2;
+    }
+  }
+  IR_TRY(res_block(c, e + ".mid.block_1", cur, H, W, C, C, true));
+  IR_TRY(attn_block(c, e + ".mid.attn_1", cur, H, W, C));
+  IR_TRY(res_block(c, e + ".mid.block_2", cur, H, W, C, C, true));
+  bf16* hn = c.w.buf[(cur + 1) & 3];
+  IR_TRY(group_norm(c, e + ".norm_out", c.w.buf[cur], hn, H * W, C, true));
+  {
+    // conv_out: 3x3, C -> 2z, fp32 output (the latents are the product of the path: no bf16 rounding here)
+    GemmArgs g;
+    g.A = hn;
+    g.W = vp<bf16>(v, e + ".conv_out.weight");
+    g.ldw = 9L * C;
+    g.M = B * H * W;
+    g.N = 2 * cfg.z_channels;
+    g.K = 9 * C;
+    g.conv = 1;
+    g.nimg = B;
+    g.H = H;
+    g.Wd = W;
+    g.C = C;
+    g.epi = EPI_F32;
+    g.bias = vp<float>(v, e + ".conv_out.bias");
+    g.out_f32 = c.w.f32tmp;
+    g.ldo_f = 2 * cfg.z_channels;
+    IR_TRY(gemm_launch(g, s));
+  }
+  IR_REQUIRE(cfg.z_channels == 4, "vae_encode: z_channels 4 expected");
+  const long P_total = (long)B * H * W;
+  moments_kernel<8><<<div_up_l(P_total, 256), 256, 0, s>>>(c.w.f32tmp, vp<float>(v, "quant_conv.weight"),
+                                                           vp<float>(v, "quant_conv.bias"), moments, P_total, H * W);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return IR_OK;
 }
 

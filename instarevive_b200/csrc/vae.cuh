@@ -1,4 +1,4 @@
-// VAE decoder handle and launcher (vae.cu).
+// VAE (decoder, optional encoder) handle and launchers (vae.cu).
 #pragma once
 #include <algorithm>
 #include <string>
@@ -15,6 +15,7 @@ struct VaeConfig {
   int out_ch = 3;
   int num_res_blocks = 2;
   int ch_mult[4] = {1, 2, 4, 4};
+  int with_encoder = 0;           // also register encoder.* / quant_conv.* (Encoder, model.py:440-546)
 };
 
 enum VaeParamKind { VP_F32 = 0, VP_CONV_BF16 = 1, VP_CONVIN_F32 = 2, VP_CONVOUT_F32 = 3 };
@@ -35,6 +36,7 @@ struct Vae {
   bf16* wb = nullptr;
   float* wf = nullptr;
   long wb_elems = 0, wf_elems = 0;
+  int first_encoder_param = -1;   // params[first_encoder_param..] belong to the encoder (decode does not need them)
 };
 
 int vae_create(const VaeConfig& cfg, Vae** out);
@@ -44,5 +46,10 @@ size_t vae_workspace_bytes(const Vae* v, int B, int h, int w);
 // z: (B,4,h,w) fp32 -> out: (B,3,8h,8w) fp32 = decode(z * in_scale) * out_scale + out_shift
 int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
                float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s);
+
+// x: (B,3,H,W) fp32 in [-1,1] -> moments: (B, 2z, H/8, W/8) fp32 = quant_conv(Encoder(x)) (mean | logvar)
+size_t vae_encode_workspace_bytes(const Vae* v, int B, int H, int W);
+int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+               cudaStream_t s);
 
 }  // namespace ir

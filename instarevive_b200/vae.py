@@ -1,8 +1,11 @@
 """Host-side mirror of the VAE surface that process() uses (test_scripts/inference.py:104-117,142):
 `vae.config.scaling_factor`, `vae.decode(z)` (diffusers style: object with `.sample`; ldm style via `decode_tensor`)
 and `vae.encode(x).latent_dist.mode()`. The decoder (`post_quant_conv` + ldm `Decoder`, ldm/models/autoencoder.py:88-91,
-ldm/modules/diffusionmodules/model.py:549-655) runs in libinstarevive_b200.so; the encoder is outside the hot path
- and is delegated to an injected callable."""
+ldm/modules/diffusionmodules/model.py:549-655) runs in libinstarevive_b200.so.
+
+`AutoencoderKLDecoder` holds the decoder only (the hot path; an encoder callable can be injected);
+`AutoencoderKL` also holds `encoder.*` / `quant_conv.*` and runs AutoencoderKL.encode (autoencoder.py:82-86,
+Encoder.forward model.py:521-546) on the same CUDA kernels -- SURVEY 8f row 1, the step right before the hot path."""
 from __future__ import annotations
 
 import ctypes as C
@@ -19,8 +22,33 @@ class DecoderOutput:
         self.sample = sample
 
 
+class DiagonalGaussianDistribution:
+    """ldm/modules/distributions/distributions.py:24-62 (the members process() and diffusers callers use)."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+
+class EncoderOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+
 class AutoencoderKLDecoder:
     """`post_quant_conv` + `decoder.*` weights (reference key names) on a CUDA device, decode through the C ABI."""
+
+    _WITH_ENCODER = False
 
     def __init__(self, state_dict: Mapping[str, torch.Tensor], device="cuda", scaling_factor: float = 0.18215,
                  ch: int = 128, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 4, out_ch: int = 3,
@@ -32,7 +60,8 @@ class AutoencoderKLDecoder:
         self._encoder = encoder
         self._ws = None
         L = _lib.lib()
-        cfg = _lib.VaeConfig(ch, z_channels, out_ch, num_res_blocks, (C.c_int * 4)(*ch_mult))
+        self._ws_enc = None
+        cfg = _lib.VaeConfig(ch, z_channels, out_ch, num_res_blocks, (C.c_int * 4)(*ch_mult), 1 if self._WITH_ENCODER else 0)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(L.ir_vae_create(C.byref(cfg), C.byref(h)), "ir_vae_create")
@@ -84,3 +113,32 @@ class AutoencoderKLDecoder:
         if self._encoder is None:
             raise NotImplementedError("the VAE encoder is outside the restoration hot path (SURVEY 8f); pass encoder=")
         return self._encoder(x)
+
+
+class AutoencoderKL(AutoencoderKLDecoder):
+    """Decoder + encoder (`encoder.*`, `quant_conv.*`) on the device; `encode(x).latent_dist.mode()` as process() calls
+    it (test_scripts/inference.py:104-109). x: (B,3,H,W) in [-1,1], H and W multiples of 16."""
+
+    _WITH_ENCODER = True
+
+    @torch.no_grad()
+    def encode_moments(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device.type != "cuda":
+            raise RuntimeError("instarevive_b200 has no CPU path: images must be CUDA tensors")
+        L = _lib.lib()
+        xx = x.to(dtype=torch.float32).contiguous()
+        B, ch, H, W = xx.shape
+        if ch != 3 or H % 16 or W % 16:
+            raise ValueError(f"encode expects (B,3,H,W) with H, W multiples of 16, got {tuple(xx.shape)}")
+        out = torch.empty(B, 8, H // 8, W // 8, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            need = L.ir_vae_encode_workspace_bytes(self._handle, B, H, W)
+            if self._ws_enc is None or self._ws_enc.numel() < need:
+                self._ws_enc = None
+                self._ws_enc = torch.empty(need, dtype=torch.uint8, device=x.device)
+            _lib.check(L.ir_vae_encode(self._handle, xx.data_ptr(), out.data_ptr(), B, H, W, self._ws_enc.data_ptr(),
+                                       self._ws_enc.numel(), _lib.stream_ptr()), "ir_vae_encode")
+        return out
+
+    def encode(self, x: torch.Tensor) -> EncoderOutput:
+        return EncoderOutput(DiagonalGaussianDistribution(self.encode_moments(x)))

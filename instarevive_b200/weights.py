@@ -143,6 +143,41 @@ def make_vae_decoder_state_dict(seed: int = 2, ch: int = 128, ch_mult=(1, 2, 4, 
     return sd
 
 
+def make_vae_encoder_state_dict(seed: int = 5, ch: int = 128, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2,
+                                z_channels: int = 4, in_channels: int = 3) -> "OrderedDict[str, torch.Tensor]":
+    """fp32 weights of ldm Encoder (ldm/modules/diffusionmodules/model.py:440-546) + `quant_conv`
+    (ldm/models/autoencoder.py:84) with the ddconfig of configs/cldm.yaml:69-84 (double_z, no attn_resolutions).
+    Keys: encoder.*, quant_conv.* (SURVEY 8f row 1)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    e = "encoder"
+    _conv(sd, gen, f"{e}.conv_in", ch, in_channels, 3)
+    block_in = ch
+    for i_level in range(len(ch_mult)):
+        block_out = ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks):
+            _resblock(sd, gen, f"{e}.down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != len(ch_mult) - 1:
+            _conv(sd, gen, f"{e}.down.{i_level}.downsample.conv", block_in, block_in, 3)
+    _resblock(sd, gen, f"{e}.mid.block_1", block_in, block_in)
+    _norm(sd, gen, f"{e}.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(sd, gen, f"{e}.mid.attn_1.{n}", block_in, block_in, 1, gain=1.0 if n != "proj_out" else 0.5)
+    _resblock(sd, gen, f"{e}.mid.block_2", block_in, block_in)
+    _norm(sd, gen, f"{e}.norm_out", block_in)
+    _conv(sd, gen, f"{e}.conv_out", 2 * z_channels, block_in, 3)
+    _conv(sd, gen, "quant_conv", 2 * z_channels, 2 * z_channels, 1)
+    return sd
+
+
+def make_vae_state_dict(dec_seed: int = 2, enc_seed: int = 5) -> "OrderedDict[str, torch.Tensor]":
+    """Decoder + encoder weights under the reference's AutoencoderKL key names."""
+    sd = make_vae_decoder_state_dict(seed=dec_seed)
+    sd.update(make_vae_encoder_state_dict(seed=enc_seed))
+    return sd
+
+
 # ---------------------------------------------------------------------------------------------- synthetic inputs
 def make_inputs(B: int, h: int, w: int, seed: int = 0, lmax: int = 120, lens=(77,), caption_channels: int = 4096):
     """Synthetic DiT inputs of SURVEY 8d: x = c = unit-scale latents, 120-token caption with `lens` valid tokens."""

@@ -1,4 +1,6 @@
-"""ORACLE (test infrastructure, not product code): fp32 CPU restatement of the reference VAE decode path,
+"""ORACLE (test infrastructure, not product code): fp32 CPU restatement of the reference VAE decode path (and, for
+SURVEY 8f row 1, of the encode path: AutoencoderKL.encode, ldm/models/autoencoder.py:82-86 -> Encoder.forward,
+ldm/modules/diffusionmodules/model.py:521-546, Downsample model.py:70-89),
 AutoencoderKL.decode (ldm/models/autoencoder.py:88-91) -> Decoder.forward (ldm/modules/diffusionmodules/model.py:622-655)
 with the ddconfig of configs/cldm.yaml:69-84 (ch 128, ch_mult (1,2,4,4), 2 res blocks, z 4, no attn_resolutions).
 
@@ -66,3 +68,25 @@ def vae_decode(sd, z, num_resolutions: int = 4, num_res_blocks: int = 2):
             h = _conv(sd, f"{d}.up.{i_level}.upsample.conv", h, 1)
     h = _swish(_gn(sd, f"{d}.norm_out", h))                              # model.py:650-652
     return _conv(sd, f"{d}.conv_out", h, 1)
+
+
+@torch.no_grad()
+def vae_encode_moments(sd, x, num_resolutions: int = 4, num_res_blocks: int = 2):
+    """Encoder.forward then quant_conv; x: (B, 3, H, W) in [-1, 1] -> moments (B, 8, H/8, W/8), fp32.
+    DiagonalGaussianDistribution.mode() (distributions.py:61-62) is moments[:, :4]."""
+    sd = {k: v.float() for k, v in sd.items()}
+    e = "encoder"
+    h = _conv(sd, f"{e}.conv_in", x.float(), 1)                          # model.py:526
+    for i_level in range(num_resolutions):                               # model.py:527-535
+        for i_block in range(num_res_blocks):
+            h = resnet_block(sd, f"{e}.down.{i_level}.block.{i_block}", h)
+        if i_level != num_resolutions - 1:                               # Downsample.forward, model.py:82-89
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv2d(h, sd[f"{e}.down.{i_level}.downsample.conv.weight"], sd[f"{e}.down.{i_level}.downsample.conv.bias"],
+                         stride=2, padding=0)
+    h = resnet_block(sd, f"{e}.mid.block_1", h)                          # model.py:538-541
+    h = attn_block(sd, f"{e}.mid.attn_1", h)
+    h = resnet_block(sd, f"{e}.mid.block_2", h)
+    h = _swish(_gn(sd, f"{e}.norm_out", h))                              # model.py:544-546
+    h = _conv(sd, f"{e}.conv_out", h, 1)
+    return _conv(sd, "quant_conv", h, 0)                                 # autoencoder.py:84

@@ -7,10 +7,11 @@ What differs, by construction of the hot-path scope:
   * the generator is ControlPixArtMSHalf on hand-written sm_100a kernels (operator surface (A)); `--ckpt` is a
     torch.save'd state_dict with the reference's keys (base_model.* / controlnet.* or bare PixArt keys), or the literal
     `random:<seed>` for the seeded random-init weights used in the parity tests (no checkpoint ships offline);
-  * the VAE decoder weights come from `--vae_ckpt` (keys post_quant_conv.*, decoder.*) or `random:<seed>`; the VAE
-    encoder and the SwinIR stage-1 model are outside the path: `--disable_preprocess_model` is implied unless a
-    TorchScript preprocess model is given, and the encoder is diffusers' AutoencoderKL when importable, otherwise the
-    synthetic stride-8 projection of instarevive_b200.weights.SyntheticVAE;
+  * the VAE weights come from `--vae_ckpt` (a state_dict with the AutoencoderKL keys post_quant_conv.*, decoder.*,
+    encoder.*, quant_conv.*) or `random:<seed>`; encode and decode both run on the sm_100a kernels
+    (instarevive_b200.AutoencoderKL). A checkpoint that holds only the decoder keys falls back to the synthetic stride-8
+    projection of instarevive_b200.weights.SyntheticVAE for the encoder. The SwinIR stage-1 model is outside the path:
+    `--disable_preprocess_model` is implied unless a TorchScript preprocess model is given;
   * the caption embedding is read from `--caption_embeds` (a .pth with 'caption_embeds' and 'emb_mask', as the
     reference loads at :256-259) or synthesised.
 """
@@ -122,15 +123,11 @@ def main() -> None:
     model.load_state_dict(_load_sd(args.ckpt, lambda s: weights.make_dit_state_dict(28, 13, seed=s)), strict=True)
     model = model.to(dev)
 
-    encoder = None
-    try:  # the real encoder when diffusers and the weights are available (reference: inference.py:236-237)
-        from diffusers.models import AutoencoderKL  # type: ignore
-        _enc = AutoencoderKL.from_pretrained("stabilityai/sd-vae-ft-ema").to(torch.float32).to(dev)
-        encoder = _enc.encode
-    except Exception:
-        encoder = weights.SyntheticVAE(None).encode
-    vae = ir.AutoencoderKLDecoder(_load_sd(args.vae_ckpt, lambda s: weights.make_vae_decoder_state_dict(seed=s)),
-                                  device=dev, encoder=encoder)
+    vae_sd = _load_sd(args.vae_ckpt, lambda s: weights.make_vae_state_dict(dec_seed=s))
+    if any(k.startswith("encoder.") for k in vae_sd):
+        vae = ir.AutoencoderKL(vae_sd, device=dev)   # encode + decode on the device (reference: inference.py:104-117)
+    else:
+        vae = ir.AutoencoderKLDecoder(vae_sd, device=dev, encoder=weights.SyntheticVAE(None).encode)
 
     preprocess_model = None
     if args.preprocess_model and not args.disable_preprocess_model:

@@ -120,6 +120,53 @@ def test_qkv_heads_and_tcgen05_attention(ctx, B, T):
     _close(out, sref.permute(0, 2, 1, 3).reshape(M, D), 1e-2)
 
 
+@pytest.mark.parametrize("B,T,qscale", [(1, 4096, 30.0), (1, 1000, 4.0), (2, 1536, 1.0), (1, 130, 8.0)])
+def test_tcgen05_attention_sharp_softmax_and_ragged_tiles(ctx, B, T, qscale):
+    """Scores far apart (exponents far below 2^-126 before the clamp of the FMA-pipe exp2 path, running max that keeps
+    growing -> O rescale in TMEM), key / query counts that are not multiples of the 128-wide tiles, and a query count
+    that leaves the second query tile of a CTA nearly empty. Reference: torch SDPA in fp32 on the same bf16 operands."""
+    _lib, L, dev = ctx
+    heads, hd = 16, 72
+    g = torch.Generator().manual_seed(B * 13 + T)
+    Tp = (T + 7) // 8 * 8
+    q = (torch.randn(B, heads, T, hd, generator=g) * qscale).to(dev).bfloat16()
+    k = torch.randn(B, heads, T, hd, generator=g).to(dev).bfloat16()
+    v = torch.randn(B, heads, T, hd, generator=g).to(dev).bfloat16()
+    vt = torch.zeros(B, heads, hd, Tp, device=dev, dtype=torch.bfloat16)
+    vt[..., :T] = v.transpose(2, 3)
+    out = torch.zeros(B * T, heads * hd, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_attention_tc_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), heads * hd, B, heads, hd, T,
+                                      Tp, hd ** -0.5, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).permute(0, 2, 1, 3).reshape(B * T, heads * hd)
+    _close(out, ref, 1e-2)
+
+
+def test_attention_trace_entry_point(ctx):
+    """ir_debug_attention_trace: the instrumented instantiation computes the same result and fills the stamp buffer."""
+    _lib, L, dev = ctx
+    heads, hd, B, T = 16, 72, 1, 512
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (torch.randn(B, heads, T, hd, generator=g).to(dev).bfloat16() for _ in range(3))
+    vt = v.transpose(2, 3).contiguous()
+    outs = []
+    n = L.ir_debug_attention_trace(None)
+    buf = torch.zeros(n, device=dev, dtype=torch.int64)
+    try:
+        for traced in (False, True):
+            L.ir_debug_attention_trace(buf.data_ptr() if traced else None)
+            out = torch.zeros(B * T, heads * hd, device=dev, dtype=torch.bfloat16)
+            _lib.check(L.ir_attention_tc_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), heads * hd, B, heads,
+                                              hd, T, T, hd ** -0.5, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        L.ir_debug_attention_trace(None)
+    assert torch.equal(outs[0], outs[1])
+    stamps = buf.cpu().view(4, -1, 8)
+    assert int(stamps[0, 0, 1]) > 0 and int(stamps[2, 0, 2]) > int(stamps[2, 0, 0]) > 0
+
+
 @pytest.mark.parametrize("B,T,lens", [(2, 1024, [120, 77]), (3, 600, [1, 300, 64]), (1, 100, [33])])
 def test_varlen_cross_attention(ctx, B, T, lens):
     _lib, L, dev = ctx

@@ -129,6 +129,48 @@ def test_vae_decode_matches_reference_golden(vae_dec, golden_dir, tag, shape, se
     assert np.abs(img - ref).max() <= 0.08  # bf16 activations through 30 layers; image range is about [-1, 1.3]
 
 
+ENC_TOL = 6e-2   # bf16 activation storage through the ~25-layer encoder stack: measured max-abs 0.040 (rms 0.007) on moments of std 0.6, |max| 3
+
+
+@pytest.fixture(scope="module")
+def vae_full():
+    import instarevive_b200 as ir
+    from instarevive_b200 import weights
+    return ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=_cuda())
+
+
+@pytest.mark.parametrize("tag", ["b1_128x128", "b2_96x160", "b1_256x256"])
+def test_vae_encode_matches_reference_golden(vae_full, golden_dir, tag):
+    """AutoencoderKL.encode(x).latent_dist.mode() on the CUDA kernels vs the reference Encoder's output
+    (stride-2 Downsample with (0,1,0,1) padding, non-square input, batch 2)."""
+    from instarevive_b200 import weights
+    dev = _cuda()
+    g = np.load(golden_dir / f"vae_enc_{tag}.npz")
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    imgs = [weights.synthetic_degraded_image(H, W, seed=int(g["img_seed"]) + i) for i in range(B)]
+    x = torch.from_numpy(np.stack(imgs)).float().div(255.0).permute(0, 3, 1, 2).contiguous() * 2 - 1
+    post = vae_full.encode(x.to(dev)).latent_dist
+    ref = torch.from_numpy(g["moments"])
+    mom = post.parameters.cpu()
+    assert mom.shape == ref.shape
+    err = (mom - ref).abs()
+    rel_rms = ((mom - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    assert err.max().item() <= ENC_TOL, f"max-abs {err.max().item():.4f}"
+    assert rel_rms <= 2e-2, f"relative RMS {rel_rms:.4f}"   # measured 1.1e-2: bf16 storage noise of ~25 layers
+    assert torch.equal(post.mode().cpu(), mom[:, :4])
+    # the decoder of the same handle still works (decode does not need the encoder weights and vice versa)
+    img = vae_full.decode(post.mode()).sample
+    assert img.shape == (B, 3, H, W) and torch.isfinite(img).all()
+
+
+def test_vae_encode_rejects_bad_input(vae_full):
+    dev = _cuda()
+    with pytest.raises(ValueError):
+        vae_full.encode(torch.zeros(1, 3, 40, 64, device=dev))
+    with pytest.raises(RuntimeError):
+        vae_full.encode(torch.zeros(1, 3, 64, 64))
+
+
 def test_vae_decode_full_tile_blockmeans(vae_dec, golden_dir):
     dev = _cuda()
     g = np.load(golden_dir / "vae_b1_64x64_blockmeans.npz")

@@ -68,3 +68,19 @@ def test_vae_oracle_matches_reference(golden_dir, tag, shape, seed):
     z = torch.randn(B, 4, h, w, generator=torch.Generator().manual_seed(seed)) / 0.18215 * 0.6
     img = vae_oracle.vae_decode(sd, z)
     assert (img - torch.from_numpy(g["img"])).abs().max().item() < 1e-4
+
+
+def _enc_image(B, H, W, seed):
+    imgs = [weights.synthetic_degraded_image(H, W, seed=seed + i) for i in range(B)]
+    return torch.from_numpy(np.stack(imgs)).float().div(255.0).permute(0, 3, 1, 2).contiguous() * 2 - 1
+
+
+@pytest.mark.parametrize("tag", ["b1_128x128", "b2_96x160", "b1_256x256"])
+def test_vae_encoder_oracle_matches_reference(golden_dir, tag):
+    """Encoder.forward + quant_conv restatement vs the reference Encoder's own output (moments)."""
+    g = _load(golden_dir, f"vae_enc_{tag}.npz")
+    sd = weights.make_vae_encoder_state_dict(seed=int(g["wseed"]))
+    moments = vae_oracle.vae_encode_moments(sd, _enc_image(int(g["B"]), int(g["H"]), int(g["W"]), int(g["img_seed"])))
+    ref = torch.from_numpy(g["moments"])
+    assert moments.shape == ref.shape
+    assert (moments - ref).abs().max().item() < 1e-4
