@@ -250,6 +250,32 @@ def run_cuda(args):
     h2d = int(host_img.numel())      # process() uploads the uint8 HWC image and normalises it on the device
     d2h = int(host_img.numel()) * 2  # restored image + stage-1 image, uint8
 
+    # SURVEY 8f row 1 (the step right before the path), measured to the same bar: the VAE encoder on the device, alone
+    # and inside process() (host uint8 image -> encode -> restore -> uint8 on the host)
+    enc_info = None
+    if not args.no_encoder:
+        vae_full = ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=dev)
+        x_img = (control * 2 - 1).contiguous()
+
+        def step_encode():
+            return vae_full.encode(x_img).latent_dist.mode()
+
+        def step_e2e_native():
+            preds, _ = ir.process(net, [host_img.numpy()], strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
+                                  tiled=tiled, tile_size=512, tile_stride=448, vae=vae_full, y=y, y_mask=mask, scheduler=sched)
+            return preds
+
+        enc_ms, _ = timed(step_encode, args.steps, 2)
+        e2e_nat_ms, _ = timed(step_e2e_native, args.steps, 1)
+        enc_flops = 4.5e12 * (side / 1024.0) ** 2   # 1.12 TFLOP per 512x512 image
+        enc_info = {"ms_per_image": enc_ms / args.steps, "tflops": enc_flops / (enc_ms / args.steps / 1e3) / 1e12,
+                    "e2e_with_native_encoder": {"value": mp_per_step * args.steps / (e2e_nat_ms / 1e3), "unit": UNIT,
+                                                "ms_per_step": e2e_nat_ms / args.steps},
+                    "note": "AutoencoderKL.encode of the whole image on the device (reference: inference.py:104-109); "
+                            "outside the north-star metric, reported beside it"}
+        del vae_full
+        torch.cuda.empty_cache()
+
     # per-kernel roofline pass: the same steps re-run with CUDA events around every launch of the GEMM family
     L = _lib.lib()
     prof = None
@@ -263,7 +289,8 @@ def run_cuda(args):
         fl = (C.c_double * 8)()
         cnt = (C.c_longlong * 8)()
         L.ir_profile_end(ms, fl, cnt)
-        prof = {"gemm": (ms[0], fl[0], cnt[0]), "conv": (ms[1], fl[1], cnt[1]), "attention": (ms[2], fl[2], cnt[2])}
+        prof = {"gemm": (ms[0], fl[0], cnt[0]), "conv": (ms[1], fl[1], cnt[1]), "attention": (ms[2], fl[2], cnt[2]),
+                "cross_attention": (ms[3], fl[3], cnt[3])}
     peak_tf, peak_hbm, peak_src = _peaks()
     # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture (profiles/)
     traffic = None
@@ -321,6 +348,7 @@ def run_cuda(args):
                     "ms_per_step": e2e_ms / args.steps, "api": "instarevive_b200.process(model, [uint8 HWC image], ...)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
             "model_tflops_per_step": flops_step / 1e12 if flops_step else None, "output_crc32": checksum,
+            "vae_encode": enc_info,
             "mfu_vs_measured_peak": (flops_step / (total_ms / args.steps / 1e3) / 1e12 / peak_tf) if flops_step else None,
         }
         print(json.dumps(line), flush=True)
@@ -340,6 +368,7 @@ def main():
     ap.add_argument("--depth", type=int, default=28)
     ap.add_argument("--copy-blocks", type=int, default=13)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the VAE-encoder side measurement (SURVEY 8f row 1)")
     args = ap.parse_args()
     if args.size is None:
         args.size = 2048 if args.workload == "tiled" else IMG

@@ -49,7 +49,8 @@ long long ir_launch_count(void);
 
 /* Per-launch timing of the tensor-core kernels (bench.py roofline pass). Between begin and end every GEMM / conv /
  * attention launch is bracketed by CUDA events on its stream; end synchronises the device and returns, per class
- * (0 = tcgen05 GEMM, 1 = tcgen05 implicit-GEMM conv, 2 = attention; arrays of 8), the summed launch durations in ms,
+ * (0 = tcgen05 GEMM, 1 = tcgen05 implicit-GEMM conv, 2 = tcgen05 self-attention, 3 = var-len cross-attention; arrays of
+ * 8), the summed launch durations in ms,
  * the summed algorithmic FLOPs and the launch counts. Not thread-safe; not for use inside CUDA-graph capture. */
 void ir_profile_begin(void);
 int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launches_by_class);

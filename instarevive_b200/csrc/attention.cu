@@ -249,7 +249,7 @@ static int launch_attn(const AttnDev& p, int B, int heads, double flops, cudaStr
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
   IR_CUDA_CHECK(launch_pdl(kern, grid, dim3(NWARPS * 32), smem, stream, p));
-  if (prof) prof_after(stream, PROF_ATTN, flops);
+  if (prof) prof_after(stream, PROF_XATTN, flops);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;

@@ -94,7 +94,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 void count_launch(int n = 1);
 
 // Optional per-launch timing (bench.py roofline pass): CUDA events around the launches of one kernel class.
-enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_NUM = 8 };
+enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_XATTN = 3, PROF_NUM = 8 };   // ATTN: tcgen05 self-attention; XATTN: var-len cross-attention
 bool prof_enabled();
 void prof_before(cudaStream_t s);
 void prof_after(cudaStream_t s, int klass, double flops);

@@ -216,8 +216,17 @@ class ControlPixArtMSHalf(nn.Module):
         return next(self.parameters()).device
 
     def load_state_dict(self, state_dict: Mapping[str, Any], strict: bool = True):
-        """Accepts full keys (base_model.* / controlnet.*) or bare PixArt keys (pixart_controlnet.py:151-163)."""
+        """Accepts full keys (base_model.* / controlnet.*) or bare PixArt keys (pixart_controlnet.py:151-163), and the
+        diffusers Transformer2DModel layout of the released checkpoints (converted by instarevive_b200.convert; the
+        PixArt buffers y_embedding / pos_embed that diffusers checkpoints do not carry keep their current values)."""
         self._packed_version = None
+        from . import convert
+        if convert.is_diffusers_layout(state_dict):
+            state_dict = convert.diffusers_to_pixart(state_dict)
+            own = self.state_dict() if any(k.startswith("base_model") for k in state_dict) else self.base_model.state_dict()
+            for k, v in own.items():
+                if k.endswith("y_embedder.y_embedding") or k.endswith("pos_embed"):
+                    state_dict.setdefault(k, v)
         if all((k.startswith("base_model") or k.startswith("controlnet")) for k in state_dict.keys()):
             return super().load_state_dict(state_dict, strict)
         return self.base_model.load_state_dict(state_dict, strict)

@@ -121,3 +121,39 @@ def test_scheduler_known_answer():
     import instarevive_b200 as ir
     s = ir.DDPMSchedulerLite()
     assert abs(float(s.alphas_cumprod[400]) - 0.19357200966664662) < 5e-7  # fp32 cumprod vs float64 known answer
+
+
+def test_diffusers_weight_layout_round_trip_and_reference_key_names():
+    """the diffusers <-> PixArt key mapping. Key names are pinned to the templates read out of the
+    reference's converter (tests/golden/diffusers_keys.json, oracle/make_goldens_convert.py); tensors must survive
+    PixArt -> diffusers -> PixArt bit-exactly (q/k/v and k/v re-fused in chunk order)."""
+    import json
+    import torch
+    from instarevive_b200 import convert, weights
+    gold = json.loads((ROOT / "tests" / "golden" / "diffusers_keys.json").read_text())
+    sd = weights.make_dit_state_dict(depth=3, copy_blocks=2, seed=4)
+    dif = convert.pixart_to_diffusers(sd)
+    assert convert.is_diffusers_layout(dif) and not convert.is_diffusers_layout(sd)
+    templ = set(gold["diffusers_keys"]) - {k for k in gold["diffusers_keys"] if "q_norm" in k or "k_norm" in k}  # qk_norm off
+    base_keys = {re.sub(r"transformer_blocks\.\d+\.", "transformer_blocks.{depth}.", k[len("base_model."):])
+                 for k in dif if k.startswith("base_model.")}
+    assert base_keys == templ, base_keys ^ templ
+    ctrl = {re.sub(r"^controlnet\.\d+\.copied_block\.", "transformer_blocks.{depth}.", k) for k in dif
+            if k.startswith("controlnet.") and ".copied_block." in k}
+    assert ctrl == {k for k in templ if k.startswith("transformer_blocks.")}
+    back = convert.diffusers_to_pixart(dif)
+    dropped = {k for k in sd if k.endswith("y_embedder.y_embedding") or k.endswith("pos_embed")}   # converter :194-198
+    assert set(back) == set(sd) - dropped
+    for k, v in back.items():
+        assert torch.equal(v, sd[k]), k
+    # bare transformer state dict (the released InstaRevive_v1.ckpt layout, test_scripts/inference.py:238-242)
+    bare = {k[len("base_model."):]: v for k, v in dif.items() if k.startswith("base_model.")}
+    back_bare = convert.diffusers_to_pixart(bare)
+    assert all(torch.equal(v, sd["base_model." + k]) for k, v in back_bare.items()) and len(back_bare) == len(bare) - 6 * 3   # per block: qkv 2 -> 6 keys, kv 2 -> 4 keys
+    # the host module loads the diffusers layout directly
+    import instarevive_b200 as ir
+    net = ir.ControlPixArtMSHalf(ir.PixArtMS(depth=3, input_size=64, micro_condition=True, init_weights=False), 2)
+    net.load_state_dict(dif, strict=True)
+    got = net.state_dict()
+    for k in back:
+        assert torch.equal(got[k], sd[k]), k
