@@ -545,6 +545,12 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   switch (key) {
     case 0: IR_TRY(launch(attn_tc_kernel<0, 0>)); break;
     case 2: IR_TRY(launch(attn_tc_kernel<2, 0>)); break;
+    case 10: IR_TRY(launch(attn_tc_kernel<0, 1>)); break;
+    case 12: IR_TRY(launch(attn_tc_kernel<2, 1>)); break;
+    case 20: IR_TRY(launch(attn_tc_kernel<0, 2>)); break;
+    case 22: IR_TRY(launch(attn_tc_kernel<2, 2>)); break;
+    case 23: IR_TRY(launch(attn_tc_kernel<3, 2>)); break;
+    case 24: IR_TRY(launch(attn_tc_kernel<4, 2>)); break;
     case 30: IR_TRY(launch(attn_tc_kernel<0, 3>)); break;
     case 32: IR_TRY(launch(attn_tc_kernel<2, 3>)); break;
     case 33: IR_TRY(launch(attn_tc_kernel<3, 3>)); break;
