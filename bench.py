@@ -171,6 +171,10 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL announces its version on stdout when NCCL_DEBUG is VERSION (some images export that); the contract is ONE
+        # JSON line on stdout, so keep warnings only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
