@@ -97,6 +97,11 @@ int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* times
 int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
                  float sqrt_one_minus_abar, void* stream);
 
+/* out = ca*x + c0*m0 + c1*m1 (m1 may be NULL), fp32, in place allowed: the state update of the multistep DPM-Solver++
+ * (diffusion/model/dpm_solver.py:551-597 first-order, :805-863 second-order). */
+int ir_lincomb3(const float* x, const float* m0, const float* m1, float* out, long long n, float ca, float c0, float c1,
+                void* stream);
+
 /* ------------------------------------------------------------------ VAE decoder ---- */
 typedef struct ir_vae ir_vae; /* opaque: packed decoder weights */
 

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "ir_debug_attention_trace": (_i, [_vp]),
     "ir_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ir_pos_embed": (_i, [_vp, _i, _i, _i, _i, _f, _vp]),
+    "ir_lincomb3": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
     "ir_vae_create": (_i, [C.POINTER(VaeConfig), C.POINTER(_vp)]),
     "ir_vae_destroy": (None, [_vp]),
     "ir_vae_num_params": (_i, [_vp]),

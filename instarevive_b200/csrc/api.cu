@@ -205,6 +205,11 @@ int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C
   return eps_to_x0_launch(x, model_out, x0, B, C, HW, sqrt_abar, sqrt_one_minus_abar, (cudaStream_t)stream);
 }
 
+int ir_lincomb3(const float* x, const float* m0, const float* m1, float* out, long long n, float ca, float c0, float c1,
+                void* stream) {
+  return lincomb3_launch(x, m0, m1, out, n, ca, c0, c1, (cudaStream_t)stream);
+}
+
 int ir_vae_create(const ir_vae_config* cfg, ir_vae** out) {
   if (!cfg || !out) {
     set_last_error("ir_vae_create: null argument");

@@ -367,6 +367,28 @@ int eps_to_x0_launch(const float* x, const float* model_out, float* x0, int B, i
   return IR_OK;
 }
 
+// DPM-Solver++ multistep update (diffusion/model/dpm_solver.py:551-597,805-863) as one fused pass:
+// out = ca * x + c0 * m0 + c1 * m1 (m1 unused when c1 == 0); in place (out == x) is allowed.
+__global__ void lincomb3_kernel(const float* __restrict__ x, const float* __restrict__ m0, const float* __restrict__ m1,
+                                float* __restrict__ out, long n, float ca, float c0, float c1) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = ca * x[i] + c0 * m0[i];
+    if (m1) v += c1 * m1[i];
+    out[i] = v;
+  }
+}
+
+int lincomb3_launch(const float* x, const float* m0, const float* m1, float* out, long n, float ca, float c0, float c1,
+                    cudaStream_t s) {
+  IR_REQUIRE(x && m0 && out && n > 0, "lincomb3: bad arguments");
+  int grid = div_up(n, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  lincomb3_kernel<<<grid, 256, 0, s>>>(x, m0, m1, out, n, ca, c0, c1);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long n4) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(x + i * 4);

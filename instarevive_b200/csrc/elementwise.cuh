@@ -41,6 +41,8 @@ int gather_rows_launch(const float* y, const int* idx, bf16* out, int rows, int 
 
 // x0 = (x - sqrt(1-abar) * eps) / sqrt(abar), eps = channels [0,C) of the (B,2C,H,W) model output.
 // scripts/DMD/transformer_train/generate.py:44-51,84-85.
+int lincomb3_launch(const float* x, const float* m0, const float* m1, float* out, long n, float ca, float c0, float c1,
+                    cudaStream_t s);
 int eps_to_x0_launch(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
                      float sqrt_one_minus_abar, cudaStream_t s);
 

@@ -157,3 +157,39 @@ def test_diffusers_weight_layout_round_trip_and_reference_key_names():
     got = net.state_dict()
     for k in back:
         assert torch.equal(got[k], sd[k]), k
+
+
+def _toy_model(x, t_input, cond, scale=1.0):
+    """Same analytic noise model as oracle/make_goldens_sampler.py (test-side torch code, not product code)."""
+    tt = t_input.view(-1, 1, 1, 1) / 1000.0
+    return scale * (0.6 * x * torch.cos(2.0 * tt) + 0.25 * torch.sin(3.0 * x + tt) + 0.1 * cond.view(-1, 1, 1, 1))
+
+
+@pytest.mark.parametrize("steps", [5, 20])
+def test_dpm_solver_schedule_and_plan_match_reference(steps):
+    """the discrete VP schedule and the multistep DPM-Solver++ plan against scalars and a trajectory
+    produced by the reference's own solver (tests/golden/dpm_plan_*.npz, oracle/make_goldens_sampler.py). The plan is
+    replayed here with plain torch on the CPU (test code); the product applies the same plan with ir_lincomb3."""
+    from instarevive_b200 import dpm_solver as ds
+    g = np.load(ROOT / "tests" / "golden" / f"dpm_plan_{steps}.npz")
+    ns = ds.NoiseScheduleVP(ds.get_named_beta_schedule_linear(1000))
+    assert ns.total_N == int(g["total_N"])
+    for t, a, s, lam in zip(g["timesteps"], g["alpha"], g["sigma"], g["lam"]):
+        assert abs(ns.marginal_alpha(float(t)) - a) <= 2e-6 * max(1.0, abs(a)) + 1e-7
+        assert abs(ns.marginal_std(float(t)) - s) <= 2e-6
+        assert abs(ns.marginal_lambda(float(t)) - lam) <= 2e-5 * max(1.0, abs(lam))
+    plan = ds.multistep_coefficients(ns, steps, order=2)
+    assert [e["order"] for e in plan] == [1] + [2] * (steps - 2) + [1]      # warm-up, ..., lower_order_final
+    assert abs(plan[0]["t_input"] - 999.0) < 1e-9 and abs(plan[0]["t"] - 1.0) < 1e-12
+    x = torch.from_numpy(g["z"]).double()
+    cond = torch.tensor([0.3, -0.7], dtype=torch.float64)
+    m_prev = None
+    for i, e in enumerate(plan):
+        eps = _toy_model(x, torch.full((2,), e["t_input"], dtype=torch.float64), cond, scale=0.9)
+        m0 = (x - e["sigma"] * eps) / e["alpha"]
+        x = e["ca"] * x + e["c0"] * m0 + (e["c1"] * m_prev if e["order"] == 2 else 0.0)
+        m_prev = m0
+        ref = torch.from_numpy(g["inter_cfg1.0"][i + 1]).double()   # intermediates[0] is the initial state
+        assert (x - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item()), f"step {i}"
+    ref_end = torch.from_numpy(g["x_end_cfg1.0"]).double()
+    assert (x - ref_end).abs().max().item() <= 2e-4 * ref_end.abs().max().item()
