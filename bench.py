@@ -279,6 +279,13 @@ def run_cuda(args):
                             "outside the north-star metric, reported beside it"}
         del vae_full
         torch.cuda.empty_cache()
+        # the stage-1 SwinIR on the same image
+        swin = ir.SwinIR(weights.make_swinir_state_dict(seed=7), device=dev)
+        swin_ms, _ = timed(lambda: swin(control), args.steps, 2)
+        enc_info["swinir_stage1"] = {"ms_per_image": swin_ms / args.steps,
+                                     "note": "SwinIR.forward (configs/swinir.yaml) of the whole image on the device"}
+        del swin
+        torch.cuda.empty_cache()
 
     # per-kernel roofline pass: the same steps re-run with CUDA events around every launch of the GEMM family
     L = _lib.lib()

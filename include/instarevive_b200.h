@@ -135,6 +135,23 @@ size_t ir_vae_encode_workspace_bytes(const ir_vae* h, int B, int H, int W);
 int ir_vae_encode(ir_vae* h, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
                   void* stream);
 
+/* ------------------------------------------------------------------ SwinIR stage 1 ---- */
+/* The `preprocess_model` of test_scripts/inference.py:92-103,245-248: diffusion/model/swinir.py SwinIR.forward (:867-905)
+ * with the parameters of configs/swinir.yaml. Parameter names are the reference's (conv_first.1.*, patch_embed.norm.*,
+ * layers.L.residual_group.blocks.B.{norm1,attn.{relative_position_bias_table,qkv,proj},norm2,mlp.{fc1,fc2}}.*,
+ * layers.L.conv.*, norm.*, conv_after_body.*, conv_before_upsample.0.*, conv_up{1,2,3}.*, conv_hr.*, conv_last.*); the
+ * buffers relative_position_index / attn_mask are functions of the window size and are not loaded.
+ * x, out: (B,3,H,W) fp32, x in [0,1]; H and W multiples of 64 (PixelUnshuffle 8 x window 8). */
+typedef struct ir_swinir ir_swinir;
+int ir_swinir_create(ir_swinir** out);
+void ir_swinir_destroy(ir_swinir* h);
+int ir_swinir_num_params(const ir_swinir* h);
+int ir_swinir_param_info(const ir_swinir* h, int i, char* name, int name_cap, long long* numel);
+int ir_swinir_load_param(ir_swinir* h, const char* name, const float* src_dev, long long numel, void* stream);
+size_t ir_swinir_workspace_bytes(const ir_swinir* h, int B, int H, int W);
+int ir_swinir_forward(ir_swinir* h, const float* x, float* out, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* ------------------------------------------------------------------ tile scheduler / pixel post-processing ---- */
 /* coords: device int32 [ntiles][2] = (hi, wi) window origins from _sliding_windows (test_scripts/inference.py:40-53),
  * multiplied by `scale` inside the kernels (1 for latents, 8 for pixels).

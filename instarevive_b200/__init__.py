@@ -6,6 +6,7 @@ from .dpm_solver import DPMS  # noqa: F401
 from .generate import DDPMSchedulerLite, eps_to_mu, forward_model, generate_sample_1step  # noqa: F401
 from .nets import ControlPixArtMSHalf, PixArtMS, PixArtMS_XL_2, PixArtMSBlock  # noqa: F401
 from .pipeline import _sliding_windows, process, restore_latents  # noqa: F401
+from .swinir import SwinIR  # noqa: F401
 from .vae import AutoencoderKL, AutoencoderKLDecoder, DiagonalGaussianDistribution  # noqa: F401
 
 __version__ = "0.1.0"

@@ -51,6 +51,13 @@ PROTOTYPES = {
     "ir_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ir_pos_embed": (_i, [_vp, _i, _i, _i, _i, _f, _vp]),
     "ir_lincomb3": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+    "ir_swinir_create": (_i, [C.POINTER(_vp)]),
+    "ir_swinir_destroy": (None, [_vp]),
+    "ir_swinir_num_params": (_i, [_vp]),
+    "ir_swinir_param_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_ll)]),
+    "ir_swinir_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
+    "ir_swinir_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "ir_swinir_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "ir_vae_create": (_i, [C.POINTER(VaeConfig), C.POINTER(_vp)]),
     "ir_vae_destroy": (None, [_vp]),
     "ir_vae_num_params": (_i, [_vp]),

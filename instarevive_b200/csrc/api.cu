@@ -9,6 +9,7 @@
 #include "../../include/instarevive_b200.h"
 #include "dit.cuh"
 #include "tiles.cuh"
+#include "swinir.cuh"
 #include "vae.cuh"
 
 namespace ir {
@@ -284,6 +285,55 @@ int ir_vae_encode(ir_vae* h, const float* x, float* moments, int B, int H, int W
     return IR_ERR_INVALID;
   }
   return vae_encode(h->v, x, moments, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ SwinIR stage 1
+struct ir_swinir {
+  Swin* s;
+};
+
+int ir_swinir_create(ir_swinir** out) {
+  if (!out) {
+    set_last_error("ir_swinir_create: null argument");
+    return IR_ERR_INVALID;
+  }
+  Swin* s = nullptr;
+  int st = swin_create(SwinConfig{}, &s);
+  if (st != IR_OK) return st;
+  *out = new ir_swinir{s};
+  return IR_OK;
+}
+void ir_swinir_destroy(ir_swinir* h) {
+  if (!h) return;
+  swin_destroy(h->s);
+  delete h;
+}
+int ir_swinir_num_params(const ir_swinir* h) { return h ? (int)h->s->params.size() : 0; }
+int ir_swinir_param_info(const ir_swinir* h, int i, char* name, int name_cap, long long* numel) {
+  if (!h || i < 0 || i >= (int)h->s->params.size() || !name || name_cap <= 0) {
+    set_last_error("ir_swinir_param_info: bad argument");
+    return IR_ERR_INVALID;
+  }
+  const SwinParam& p = h->s->params[i];
+  snprintf(name, (size_t)name_cap, "%s", p.name.c_str());
+  if (numel) *numel = p.numel;
+  return IR_OK;
+}
+int ir_swinir_load_param(ir_swinir* h, const char* name, const float* src_dev, long long numel, void* stream) {
+  if (!h || !name || !src_dev) {
+    set_last_error("ir_swinir_load_param: null argument");
+    return IR_ERR_INVALID;
+  }
+  return swin_load_param(h->s, name, src_dev, numel, (cudaStream_t)stream);
+}
+size_t ir_swinir_workspace_bytes(const ir_swinir* h, int B, int H, int W) { return h ? swin_workspace_bytes(h->s, B, H, W) : 0; }
+int ir_swinir_forward(ir_swinir* h, const float* x, float* out, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!h) {
+    set_last_error("ir_swinir_forward: null handle");
+    return IR_ERR_INVALID;
+  }
+  return swin_forward(h->s, x, out, B, H, W, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ir_tile_gather(const float* src, float* dst, const int32_t* coords, int ntiles, int N, int C, int H, int W, int th,

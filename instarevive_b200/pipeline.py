@@ -210,7 +210,7 @@ def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fi
     control = control.permute(0, 3, 1, 2).contiguous()
     if not disable_preprocess_model:
         if preprocess_model is None:
-            raise ValueError("preprocess_model (SwinIR stage 1) is outside this library; pass one or disable it")
+            raise ValueError("disable_preprocess_model is False but no preprocess_model (e.g. instarevive_b200.SwinIR) was given")
         control = preprocess_model(control)
     control_norm = control * 2 - 1
     c_latent = vae.encode(control_norm).latent_dist.mode().to(torch.float32)

@@ -178,6 +178,44 @@ def make_vae_state_dict(dec_seed: int = 2, enc_seed: int = 5) -> "OrderedDict[st
     return sd
 
 
+# ---------------------------------------------------------------------------------------------- SwinIR stage 1
+def make_swinir_state_dict(seed: int = 7, embed_dim: int = 180, depths=(6,) * 8, num_heads: int = 6, window: int = 8,
+                           mlp_ratio: int = 2, in_chans: int = 3, unshuffle: int = 8, num_feat: int = 64
+                           ) -> "OrderedDict[str, torch.Tensor]":
+    """fp32 parameters of the stage-1 SwinIR (diffusion/model/swinir.py:629-825 with configs/swinir.yaml: embed 180,
+    8 RSTB x 6 blocks, 6 heads, window 8, mlp_ratio 2, pixel-unshuffle 8, 'nearest+conv' upsampler, '1conv'). Keys are the
+    reference's parameter names; the buffers (relative_position_index, attn_mask) are functions of the window size.
+    Scales keep the 48-block residual stream O(1) so that every branch matters in the parity tests."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    C, hid = embed_dim, embed_dim * mlp_ratio
+
+    def lin(name, cout, cin, gain=1.0):
+        sd[f"{name}.weight"] = torch.randn(cout, cin, generator=gen) * (gain / math.sqrt(cin))
+        sd[f"{name}.bias"] = _normal(gen, cout, std=0.02)
+
+    _conv(sd, gen, "conv_first.1", C, in_chans * unshuffle * unshuffle, 3)
+    _norm(sd, gen, "patch_embed.norm", C)
+    for li, depth in enumerate(depths):
+        for bi in range(depth):
+            p = f"layers.{li}.residual_group.blocks.{bi}"
+            _norm(sd, gen, f"{p}.norm1", C)
+            sd[f"{p}.attn.relative_position_bias_table"] = torch.randn((2 * window - 1) ** 2, num_heads, generator=gen) * 0.5
+            lin(f"{p}.attn.qkv", 3 * C, C)
+            lin(f"{p}.attn.proj", C, C, gain=0.4)
+            _norm(sd, gen, f"{p}.norm2", C)
+            lin(f"{p}.mlp.fc1", hid, C)
+            lin(f"{p}.mlp.fc2", C, hid, gain=0.4)
+        _conv(sd, gen, f"layers.{li}.conv", C, C, 3, gain=0.4)
+    _norm(sd, gen, "norm", C)
+    _conv(sd, gen, "conv_after_body", C, C, 3, gain=0.5)
+    _conv(sd, gen, "conv_before_upsample.0", num_feat, C, 3)
+    for n in ("conv_up1", "conv_up2", "conv_up3", "conv_hr"):
+        _conv(sd, gen, n, num_feat, num_feat, 3, gain=1.3)
+    _conv(sd, gen, "conv_last", in_chans, num_feat, 3, gain=0.5)
+    return sd
+
+
 # ---------------------------------------------------------------------------------------------- synthetic inputs
 def make_inputs(B: int, h: int, w: int, seed: int = 0, lmax: int = 120, lens=(77,), caption_channels: int = 4096):
     """Synthetic DiT inputs of SURVEY 8d: x = c = unit-scale latents, 120-token caption with `lens` valid tokens."""

@@ -10,8 +10,10 @@ What differs, by construction of the hot-path scope:
   * the VAE weights come from `--vae_ckpt` (a state_dict with the AutoencoderKL keys post_quant_conv.*, decoder.*,
     encoder.*, quant_conv.*) or `random:<seed>`; encode and decode both run on the sm_100a kernels
     (instarevive_b200.AutoencoderKL). A checkpoint that holds only the decoder keys falls back to the synthetic stride-8
-    projection of instarevive_b200.weights.SyntheticVAE for the encoder. The SwinIR stage-1 model is outside the path:
-    `--disable_preprocess_model` is implied unless a TorchScript preprocess model is given;
+    projection of instarevive_b200.weights.SyntheticVAE for the encoder. The SwinIR stage-1 model (reference:
+    ./weights/general_swinir_v1.ckpt, inference.py:245-248) runs on the sm_100a kernels too (instarevive_b200.SwinIR) from
+    `--swinir_ckpt` (a state_dict with the reference's keys, or `random:<seed>`); without it
+    `--disable_preprocess_model` is implied;
   * the caption embedding is read from `--caption_embeds` (a .pth with 'caption_embeds' and 'emb_mask', as the
     reference loads at :256-259) or synthesised.
 """
@@ -62,7 +64,8 @@ def parse_args() -> Namespace:
     # additions of this implementation
     p.add_argument("--vae_ckpt", type=str, default="random:2")
     p.add_argument("--caption_embeds", type=str, default=None)
-    p.add_argument("--preprocess_model", type=str, default=None, help="TorchScript stage-1 model (optional)")
+    p.add_argument("--swinir_ckpt", type=str, default=None,
+                   help="stage-1 SwinIR state_dict (reference keys) or random:<seed>; omitted = stage 1 disabled")
     return p.parse_args()
 
 
@@ -130,8 +133,8 @@ def main() -> None:
         vae = ir.AutoencoderKLDecoder(vae_sd, device=dev, encoder=weights.SyntheticVAE(None).encode)
 
     preprocess_model = None
-    if args.preprocess_model and not args.disable_preprocess_model:
-        preprocess_model = torch.jit.load(args.preprocess_model, map_location=dev).eval()
+    if args.swinir_ckpt and not args.disable_preprocess_model:
+        preprocess_model = ir.SwinIR(_load_sd(args.swinir_ckpt, lambda s: weights.make_swinir_state_dict(seed=s)), device=dev)
     disable_pre = args.disable_preprocess_model or preprocess_model is None
 
     if args.caption_embeds:

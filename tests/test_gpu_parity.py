@@ -288,6 +288,42 @@ def test_tiled_restore_sharding_is_bit_identical(vae_dec):
     assert float(full.min()) > -0.5 and float(full.max()) < 1.5
 
 
+@pytest.fixture(scope="module")
+def swinir_net():
+    import instarevive_b200 as ir
+    from instarevive_b200 import weights
+    return ir.SwinIR(weights.make_swinir_state_dict(seed=7), device=_cuda())
+
+
+@pytest.mark.parametrize("tag", ["b1_128x128", "b2_64x192", "b1_256x256"])
+def test_swinir_matches_reference_golden(swinir_net, golden_dir, tag):
+    """the stage-1 SwinIR on the CUDA kernels vs the reference class's output on the same seeded
+    weights and images (bf16 GEMM operands, fp32 residual stream). Tolerance: PSNR >= 45 dB on the [0,1] image, as for
+    the decoder; max-abs stated from the measurement."""
+    from instarevive_b200 import weights
+    dev = _cuda()
+    g = np.load(golden_dir / f"swinir_{tag}.npz")
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    imgs = [weights.synthetic_degraded_image(H, W, seed=int(g["img_seed"]) + i) for i in range(B)]
+    x = torch.from_numpy(np.stack(imgs)).float().div(255.0).permute(0, 3, 1, 2).contiguous()
+    out = swinir_net(x.to(dev)).cpu().numpy()
+    ref = g["out"]
+    assert out.shape == ref.shape
+    p = psnr(np.clip(out, 0, 1), np.clip(ref, 0, 1), 1.0)
+    err = np.abs(out - ref).max()
+    print(f"swinir {tag}: PSNR {p:.2f} dB, max-abs {err:.4f}")
+    assert p >= PSNR_MIN, f"PSNR {p:.2f} dB"
+    assert err <= 3e-2, f"max-abs {err:.4f}"
+
+
+def test_swinir_rejects_bad_input(swinir_net):
+    dev = _cuda()
+    with pytest.raises(ValueError):
+        swinir_net(torch.zeros(1, 3, 96, 64, device=dev))
+    with pytest.raises(RuntimeError):
+        swinir_net(torch.zeros(1, 3, 64, 64))
+
+
 def test_full_size_properties_1024(vae_dec):
     """BASELINE.json configs[1] at full size (1024x1024, 28+13 blocks, T = 4096), where the CPU oracle is too slow to
     be the checker: size-independent properties instead. (i) the restore is deterministic run to run, (ii) a sample's

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from instarevive_b200 import weights
-from oracle import dit_oracle, tiles_oracle, vae_oracle
+from oracle import dit_oracle, swinir_oracle, tiles_oracle, vae_oracle
 
 torch.set_grad_enabled(False)
 
@@ -84,3 +84,17 @@ def test_vae_encoder_oracle_matches_reference(golden_dir, tag):
     ref = torch.from_numpy(g["moments"])
     assert moments.shape == ref.shape
     assert (moments - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["b1_128x128", "b2_64x192", "b1_256x256"])
+def test_swinir_oracle_matches_reference(golden_dir, tag):
+    """SwinIR.forward restatement vs the reference class's own output (window shift + mask, relative
+    position bias, RSTB convs, nearest+conv upsampler; batch 2 and a non-square image)."""
+    g = _load(golden_dir, f"swinir_{tag}.npz")
+    sd = weights.make_swinir_state_dict(seed=int(g["wseed"]))
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    imgs = [weights.synthetic_degraded_image(H, W, seed=int(g["img_seed"]) + i) for i in range(B)]
+    x = torch.from_numpy(np.stack(imgs)).float().div(255.0).permute(0, 3, 1, 2).contiguous()
+    out = swinir_oracle.swinir_forward(sd, x)
+    assert out.shape == (B, 3, H, W)
+    assert (out - torch.from_numpy(g["out"])).abs().max().item() < 1e-4
