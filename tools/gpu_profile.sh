@@ -1,18 +1,24 @@
 #!/bin/bash
 # ncu evidence for profiles/ (run on a B200 through gpurun): the bench command first exits 0 WITHOUT ncu, then
 #  (1) launch list of one resident step (bench.py brackets it with cudaProfilerStart/Stop, outside every timed region)
-#  (2) one `--set full` capture of a few launches of the tensor-core kernels (attention + GEMM/conv)
+#  (2) `--set full` captures of a few launches per kernel family (attention, DiT GEMMs, convs, GroupNorm apply, LN)
 # usage: tools/gpu_profile.sh TAG [bench args...]
 set -u
 TAG=$1; shift
 OUT=gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline $*"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-encoder $*"
 timeout 300 $CMD > $OUT/prof_${TAG}_plain.json 2> $OUT/prof_${TAG}_plain.err || { echo "plain run failed"; exit 1; }
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
   --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/prof_${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:'attn_tc_kernel|gemm_tc_kernel|gn_apply_kernel|ln_modulate_kernel' --launch-skip 40 --launch-count 36 \
-  -o $OUT/full_${TAG} -f $CMD > $OUT/prof_${TAG}_ncu2.log 2>&1
-echo "set full rc=$?"
-ls -la $OUT/full_${TAG}.ncu-rep $OUT/launches_${TAG}.csv
+full() {  # name, kernel regex, launch-skip, launch-count
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:"$2" --launch-skip $3 --launch-count $4 -o $OUT/full_${TAG}_$1 -f $CMD > $OUT/prof_${TAG}_ncu_$1.log 2>&1
+  echo "set full $1 rc=$?"
+}
+full attn 'attn_tc_kernel' 20 2
+full gemm 'gemm_tc_kernel' 120 12
+full conv 'gemm_tc_kernel' 280 8
+full gn 'gn_apply_kernel' 22 6
+full ln 'ln_modulate_kernel|flash_attn_kernel' 40 4
+ls -la $OUT/full_${TAG}_*.ncu-rep $OUT/launches_${TAG}.csv
