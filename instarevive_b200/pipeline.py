@@ -124,6 +124,25 @@ def to_uint8_nhwc(img: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_pinned: dict = {}
+
+
+def _to_host_pair(a: torch.Tensor, b: torch.Tensor):
+    """Both uint8 results to the host through one cached page-locked staging buffer (two async copies, one stream
+    synchronise); the returned arrays are fresh copies, so callers may keep them across calls."""
+    key = (tuple(a.shape), tuple(b.shape), a.device.index)
+    buf = _pinned.get(key)
+    if buf is None:
+        if len(_pinned) > 4:
+            _pinned.clear()
+        buf = _pinned[key] = (torch.empty(a.shape, dtype=torch.uint8, pin_memory=True),
+                              torch.empty(b.shape, dtype=torch.uint8, pin_memory=True))
+    buf[0].copy_(a, non_blocking=True)
+    buf[1].copy_(b, non_blocking=True)
+    torch.cuda.current_stream(a.device).synchronize()
+    return buf[0].numpy().copy(), buf[1].numpy().copy()
+
+
 _default_scheduler: Optional[DDPMSchedulerLite] = None
 
 
@@ -218,6 +237,5 @@ def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fi
     img = restore_latents(model, vae, control, init_noise, y, y_mask, tiled=tiled, tile_size=tile_size,
                           tile_stride=tile_stride, color_fix_type=color_fix_type, scheduler=scheduler,
                           decode_batch=decode_batch, group=group)
-    x_samples = to_uint8_nhwc(img).cpu().numpy()
-    stage1 = to_uint8_nhwc(control).cpu().numpy()
+    x_samples, stage1 = _to_host_pair(to_uint8_nhwc(img), to_uint8_nhwc(control))
     return [x_samples[i] for i in range(n_samples)], [stage1[i] for i in range(n_samples)]
