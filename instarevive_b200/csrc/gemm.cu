@@ -51,6 +51,7 @@ struct GemmDev {
   int M, N, K;
   int k_blocks;    // K-blocks per tile
   int raster_n;    // tile order: 1 = N blocks fastest, 0 = M blocks fastest
+  int gelu_erf;    // EPI_BF16_GELU: 1 = exact erf GELU, 0 = tanh approximation
   int m_blocks;    // 128-row M tiles per batch entry (per image for conv)
   int m_units;     // scheduling units per batch entry: m_blocks (CG 1) or ceil(m_blocks / 2) pairs (CG 2)
   int n_blocks;
@@ -484,10 +485,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a.z = a.z * p.alpha + bias4.z;
             a.w = a.w * p.alpha + bias4.w;
             if (EPI == EPI_BF16_GELU) {
-              a.x = gelu_tanh_fast(a.x);
-              a.y = gelu_tanh_fast(a.y);
-              a.z = gelu_tanh_fast(a.z);
-              a.w = gelu_tanh_fast(a.w);
+              if (p.gelu_erf) {   // exact GELU (nn.GELU default: SwinIR's Mlp); warp-uniform branch
+                a.x = 0.5f * a.x * (1.0f + erff(a.x * 0.70710678118654752f));
+                a.y = 0.5f * a.y * (1.0f + erff(a.y * 0.70710678118654752f));
+                a.z = 0.5f * a.z * (1.0f + erff(a.z * 0.70710678118654752f));
+                a.w = 0.5f * a.w * (1.0f + erff(a.w * 0.70710678118654752f));
+              } else {            // tanh approximation (PixArt's Mlp, approximate="tanh")
+                a.x = gelu_tanh_fast(a.x);
+                a.y = gelu_tanh_fast(a.y);
+                a.z = gelu_tanh_fast(a.z);
+                a.w = gelu_tanh_fast(a.w);
+              }
             }
             if (EPI == EPI_F32) {
               const long o = (long)b * p.stride_of + row_off[i] * p.ldo_f + col;
@@ -794,6 +802,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     static const int nomma = [] { const char* e = getenv("IR_GEMM_NOMMA"); return (e && e[0] == '1') ? 1 : 0; }();
     p.dbg_nomma = nomma;
   }
+  p.gelu_erf = a.gelu_erf;
   p.out_bf16 = a.out_bf16;
   p.resid_bf16 = a.resid_bf16;
   p.ldo_b = a.ldo_b;

@@ -6,7 +6,7 @@ namespace ir {
 
 enum GemmEpilogue {
   EPI_BF16 = 0,       // out_bf16 = alpha*acc + bias (+ resid_bf16)
-  EPI_BF16_GELU = 1,  // out_bf16 = gelu_tanh(alpha*acc + bias)
+  EPI_BF16_GELU = 1,  // out_bf16 = gelu(alpha*acc + bias): tanh approximation, or exact erf with GemmArgs::gelu_erf
   EPI_F32 = 2,        // out_f32 = resid_f32 + gate * (alpha*acc + bias); optional bf16 copy of out_f32
   EPI_QKV = 3,        // attn.qkv projection scattered head-major for the tcgen05 attention kernel:
                       //   q, k -> [B][H][T][hd] bf16, v -> transposed [B][H][hd][Tp] bf16 (acc + bias)
@@ -29,6 +29,7 @@ struct GemmArgs {
   int nimg = 0, H = 0, Wd = 0, C = 0;
 
   int epi = EPI_BF16;
+  int gelu_erf = 0;   // EPI_BF16_GELU only
   float alpha = 1.0f;
   const float* bias = nullptr;  // [N]
   long stride_bias = 0;         // batch stride of bias in elements

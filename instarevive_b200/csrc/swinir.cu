@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) swin_ln_kernel(const float* __restrict__ 
                                                       int C) {
   const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch();
   if (row >= rows) return;
   const float* xr = x + row * CP;
   float v[6];
@@ -78,80 +80,164 @@ __global__ void __launch_bounds__(256) swin_ln_kernel(const float* __restrict__ 
   }
 }
 
+// ---- warp-level tensor-core helpers (mma.sync m16n8k16, ldmatrix) for the 64-token windows
+IR_DEVINL void sw_ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+IR_DEVINL void sw_ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+IR_DEVINL void sw_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 // Window attention (WindowAttention.forward, swinir.py:125-156) for window 8 and head_dim 30, fused with window_partition /
 // window_reverse (:44-73), the cyclic shift (:261-265, 282-286), the relative-position bias and the shift mask (:227-248).
-// grid = (windows * B, heads), block = 64 threads: thread i owns query token i of the window.
-__global__ void __launch_bounds__(64) swin_window_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                              const float* __restrict__ bias /* [heads][64][64] */, int H,
-                                                              int W, int C, int heads, int shift, float scale) {
-  constexpr int WS = 8, N = 64, HDIM = 30;
-  __shared__ float sk[N][HDIM + 1], sv[N][HDIM + 1];
+// grid = (windows * B, heads), block = 4 warps: warp w owns query tokens [16w, 16w+16) of the window; S = q k^T and P v run
+// on mma.sync (head_dim padded to 32 with zeros), softmax in registers (a row lives in one lane quad).
+__global__ void __launch_bounds__(128) swin_window_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                               const float* __restrict__ bias /* [heads][64][64] */, int H,
+                                                               int W, int C, int heads, int shift, float scale) {
+  constexpr int WS = 8, N = 64, HDIM = 30, LDS_ = 40;   // smem row stride in bf16 (80 B: conflict-free ldmatrix)
+  __shared__ __align__(16) bf16 sq[N * LDS_], sk[N * LDS_], sv[N * LDS_];
   __shared__ int sreg[N];
+  __shared__ long stok[N];
   const int head = blockIdx.y;
   const int nwx = W / WS, nw = (H / WS) * nwx;
   const int b = blockIdx.x / nw, wi = blockIdx.x % nw;
   const int wy = wi / nwx, wx = wi % nwx;
-  const int i = threadIdx.x;
-  const int sy = wy * WS + i / WS, sx = wx * WS + i % WS;       // coordinates in the shifted image
-  const int y = (sy + shift) % H, x = (sx + shift) % W;         // torch.roll(x, -shift): shifted[sy] = x[(sy + shift) % H]
-  const long tok = ((long)b * H + y) * W + x;
-  const bf16* row = qkv + tok * (3L * C) + head * HDIM;
-  float q[HDIM];
-#pragma unroll
-  for (int d = 0; d < HDIM; ++d) {
-    q[d] = __bfloat162float(row[d]) * scale;
-    sk[i][d] = __bfloat162float(row[C + d]);
-    sv[i][d] = __bfloat162float(row[2 * C + d]);
-  }
-  if (shift > 0) {   // calculate_mask: region id of the token in the shifted image
-    const int ry = sy < H - WS ? 0 : (sy < H - shift ? 1 : 2);
-    const int rx = sx < W - WS ? 0 : (sx < W - shift ? 1 : 2);
-    sreg[i] = ry * 3 + rx;
-  } else {
-    sreg[i] = 0;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_wait();
+  pdl_launch();
+  if (tid < N) {
+    const int sy = wy * WS + tid / WS, sx = wx * WS + tid % WS;   // coordinates in the shifted image
+    const int y = (sy + shift) % H, x = (sx + shift) % W;         // torch.roll(x, -shift): shifted[sy] = x[(sy + shift) % H]
+    stok[tid] = ((long)b * H + y) * W + x;
+    int reg = 0;
+    if (shift > 0) {   // calculate_mask: region id of the token in the shifted image
+      const int ry = sy < H - WS ? 0 : (sy < H - shift ? 1 : 2);
+      const int rx = sx < W - WS ? 0 : (sx < W - shift ? 1 : 2);
+      reg = ry * 3 + rx;
+    }
+    sreg[tid] = reg;
   }
   __syncthreads();
-  const float* brow = bias + ((long)head * N + i) * N;
-  const int myreg = sreg[i];
-  float s[N];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    float a = 0.f;
-#pragma unroll
-    for (int d = 0; d < HDIM; ++d) a += q[d] * sk[j][d];
-    a += brow[j];
-    if (sreg[j] != myreg) a += -100.0f;
-    s[j] = a;
-    mx = fmaxf(mx, a);
+  // q, k, v rows of this head (30 bf16 = 15 words each) -> shared memory rows of 20 words, words 15..19 zero
+  for (int i = tid; i < N * 3 * 20; i += 128) {
+    const int wd = i % 20, which = (i / 20) % 3, r = i / 60;
+    uint32_t v = 0u;
+    if (wd < HDIM / 2) v = *reinterpret_cast<const uint32_t*>(qkv + stok[r] * (3L * C) + which * C + head * HDIM + wd * 2);
+    bf16* dst = which == 0 ? sq : (which == 1 ? sk : sv);
+    *reinterpret_cast<uint32_t*>(dst + r * LDS_ + wd * 2) = v;
   }
-  float sum = 0.f;
+  __syncthreads();
+  // ---- S = Q K^T (16 query rows of this warp x 64 keys)
+  uint32_t qf[2][4];
+  {
+    const int r = warp * 16 + (lane & 15), cbase = (lane >> 4) * 8;
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    s[j] = __expf(s[j] - mx);
-    sum += s[j];
+    for (int kk = 0; kk < 2; ++kk) sw_ldsm_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(sq + r * LDS_ + kk * 16 + cbase));
   }
-  const float inv = 1.0f / sum;
-  float o[HDIM];
+  float sc[8][4];
 #pragma unroll
-  for (int d = 0; d < HDIM; ++d) o[d] = 0.f;
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const float pj = s[j] * inv;
+    for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
 #pragma unroll
-    for (int d = 0; d < HDIM; ++d) o[d] += pj * sv[j][d];
+  for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const int kr = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+      const int kc = kk * 16 + ((lane >> 3) & 1) * 8;
+      uint32_t b0, b1, b2, b3;
+      sw_ldsm_x4(b0, b1, b2, b3, smem_u32(sk + kr * LDS_ + kc));
+      sw_mma(sc[2 * np], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
+      sw_mma(sc[2 * np + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
+    }
   }
-  bf16* orow = out + tok * CP + head * HDIM;   // window_reverse + roll(+shift): back to the token's own position
+  // ---- scale, relative-position bias, shift mask, softmax (rows r0 = lane/4 and r0 + 8 of the warp's 16)
+  const int r0 = warp * 16 + (lane >> 2);
+  const float* bias0 = bias + ((long)head * N + r0) * N;
+  const float* bias1 = bias0 + 8 * N;
+  const int reg0 = sreg[r0], reg1 = sreg[r0 + 8];
+  float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int d = 0; d < HDIM; ++d) orow[d] = __float2bfloat16(o[d]);
-  if (head == 0) {   // keep the pad columns of the 192-wide row at zero
-    for (int c = C; c < CP; ++c) out[tok * CP + c] = __float2bfloat16(0.f);
+  for (int i = 0; i < 8; ++i) {
+    const int col = i * 8 + (lane & 3) * 2;
+    const float2 bb0 = *reinterpret_cast<const float2*>(bias0 + col), bb1 = *reinterpret_cast<const float2*>(bias1 + col);
+    const int rc0 = sreg[col], rc1 = sreg[col + 1];
+    sc[i][0] = sc[i][0] * scale + bb0.x + (rc0 != reg0 ? -100.0f : 0.f);
+    sc[i][1] = sc[i][1] * scale + bb0.y + (rc1 != reg0 ? -100.0f : 0.f);
+    sc[i][2] = sc[i][2] * scale + bb1.x + (rc0 != reg1 ? -100.0f : 0.f);
+    sc[i][3] = sc[i][3] * scale + bb1.y + (rc1 != reg1 ? -100.0f : 0.f);
+    mx0 = fmaxf(mx0, fmaxf(sc[i][0], sc[i][1]));
+    mx1 = fmaxf(mx1, fmaxf(sc[i][2], sc[i][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i][0] = __expf(sc[i][0] - mx0);
+    sc[i][1] = __expf(sc[i][1] - mx0);
+    sc[i][2] = __expf(sc[i][2] - mx1);
+    sc[i][3] = __expf(sc[i][3] - mx1);
+    sum0 += sc[i][0] + sc[i][1];
+    sum1 += sc[i][2] + sc[i][3];
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  // ---- O = P V (P stays in registers as the A fragments)
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t a0 = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+    const uint32_t a1 = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+    const uint32_t a2 = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+    const uint32_t a3 = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+    const int vr = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      const int vc = np * 16 + (lane >> 4) * 8;
+      uint32_t b0, b1, b2, b3;
+      sw_ldsm_x4_t(b0, b1, b2, b3, smem_u32(sv + vr * LDS_ + vc));
+      sw_mma(o[2 * np], a0, a1, a2, a3, b0, b1);
+      sw_mma(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+  // ---- window_reverse + roll(+shift): every token goes back to its own position; d 30, 31 are padding
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const long tok = stok[r0 + h2 * 8];
+    const float inv = h2 == 0 ? inv0 : inv1;
+    bf16* orow = out + tok * CP + head * HDIM + (lane & 3) * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 8 + (lane & 3) * 2 < HDIM)
+        *reinterpret_cast<uint32_t*>(orow + i * 8) = pack_bf16x2(o[i][2 * h2] * inv, o[i][2 * h2 + 1] * inv);
+    }
+  }
+  if (head == 0) {   // keep the pad columns of the 192-wide rows at zero
+    for (int i = tid; i < N * (CP - 180); i += 128) out[stok[i / (CP - 180)] * CP + 180 + i % (CP - 180)] = __float2bfloat16(0.f);
   }
 }
 
 // exact GELU (nn.GELU default, erf) in place on rows of HP elements; the pad columns are (re)zeroed
 __global__ void __launch_bounds__(256) swin_gelu_kernel(bf16* __restrict__ h, long rows, int hidden) {
   const long total = rows * HP;
+  pdl_wait();
+  pdl_launch();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % HP);
     float v = 0.f;
@@ -164,10 +250,18 @@ __global__ void __launch_bounds__(256) swin_gelu_kernel(bf16* __restrict__ h, lo
 }
 
 // LeakyReLU in place on a bf16 tensor
-__global__ void __launch_bounds__(256) swin_lrelu_kernel(bf16* __restrict__ x, long n, float slope) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = __bfloat162float(x[i]);
-    x[i] = __float2bfloat16(v >= 0.f ? v : v * slope);
+__global__ void __launch_bounds__(256) swin_lrelu_kernel(bf16* __restrict__ x, long n8, float slope) {
+  pdl_wait();
+  pdl_launch();
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = unpack_bf16x2(w[k]);
+      w[k] = pack_bf16x2(a.x >= 0.f ? a.x : a.x * slope, a.y >= 0.f ? a.y : a.y * slope);
+    }
+    *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -327,6 +421,7 @@ int linear(SCtx& c, const std::string& name, const bf16* A, long lda, int M, int
   g.N = N;
   g.K = K;
   g.epi = epi;
+  g.gelu_erf = 1;   // SwinIR's Mlp uses nn.GELU (erf)
   g.bias = sp<float>(c.s, name + ".bias");
   g.out_bf16 = out_b;
   g.ldo_b = ldo_b;
@@ -367,10 +462,10 @@ int conv3(SCtx& c, const std::string& name, const bf16* x, int B, int H, int W, 
 }
 
 int lrelu(SCtx& c, bf16* x, long n, float slope) {
-  int grid = div_up_l(n, 256);
+  IR_REQUIRE(n % 8 == 0, "lrelu: element count must be a multiple of 8");
+  int grid = div_up_l(n / 8, 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  swin_lrelu_kernel<<<grid, 256, 0, c.st>>>(x, n, slope);
-  IR_CUDA_CHECK(cudaGetLastError());
+  IR_CUDA_CHECK(launch_pdl(swin_lrelu_kernel, dim3(grid), dim3(256), 0, c.st, x, n / 8, slope));
   count_launch();
   return IR_OK;
 }
@@ -497,9 +592,8 @@ int swin_forward(Swin* s, const float* x, float* out, int B, int H, int W, void*
   // conv_first (swinir.py:883) -> x_first (fp32, kept for the long skip)
   IR_TRY(conv3(c, "conv_first.1", c.w.img, B, h, w, Cin0, C, nullptr, 0, c.w.first, CP, nullptr));
   // patch_embed (flatten + LayerNorm, :535-539) -> residual stream x
-  swin_ln_kernel<false><<<div_up_l(L, 8), 256, 0, st>>>(c.w.first, c.w.x, sp<float>(s, "patch_embed.norm.weight"),
-                                                        sp<float>(s, "patch_embed.norm.bias"), L, C);
-  IR_CUDA_CHECK(cudaGetLastError());
+  IR_CUDA_CHECK(launch_pdl(swin_ln_kernel<false>, dim3(div_up_l(L, 8)), dim3(256), 0, st, (const float*)c.w.first, (void*)c.w.x,
+                           sp<float>(s, "patch_embed.norm.weight"), sp<float>(s, "patch_embed.norm.bias"), L, C));
   count_launch();
   const float scale = 1.0f / sqrtf((float)(C / cfg.heads));
   const int nwin = (h / cfg.window) * (w / cfg.window);
@@ -508,20 +602,16 @@ int swin_forward(Swin* s, const float* x, float* out, int B, int H, int W, void*
     for (int bi = 0; bi < cfg.depth; ++bi) {
       const std::string p = "layers." + std::to_string(l) + ".residual_group.blocks." + std::to_string(bi);
       const int shift = (bi % 2 == 0) ? 0 : cfg.window / 2;
-      swin_ln_kernel<true><<<div_up_l(L, 8), 256, 0, st>>>(c.w.x, c.w.xn, sp<float>(s, p + ".norm1.weight"),
-                                                           sp<float>(s, p + ".norm1.bias"), L, C);
-      IR_CUDA_CHECK(cudaGetLastError());
+      IR_CUDA_CHECK(launch_pdl(swin_ln_kernel<true>, dim3(div_up_l(L, 8)), dim3(256), 0, st, (const float*)c.w.x, (void*)c.w.xn,
+                               sp<float>(s, p + ".norm1.weight"), sp<float>(s, p + ".norm1.bias"), L, C));
       IR_TRY(linear(c, p + ".attn.qkv", c.w.xn, CP, (int)L, 3 * C, CP, EPI_BF16, c.w.qkv, 3L * C, nullptr, nullptr));
-      swin_window_attn_kernel<<<dim3(nwin * B, cfg.heads), 64, 0, st>>>(c.w.qkv, c.w.att, sp<float>(s, p + ".attn.relative_position_bias_table"),
-                                                                         h, w, C, cfg.heads, shift, scale);
-      IR_CUDA_CHECK(cudaGetLastError());
+      IR_CUDA_CHECK(launch_pdl(swin_window_attn_kernel, dim3(nwin * B, cfg.heads), dim3(128), 0, st, (const bf16*)c.w.qkv, c.w.att,
+                               sp<float>(s, p + ".attn.relative_position_bias_table"), h, w, C, cfg.heads, shift, scale));
       IR_TRY(linear(c, p + ".attn.proj", c.w.att, CP, (int)L, C, CP, EPI_F32, nullptr, 0, c.w.x, c.w.x));   // x += proj(attn)
-      swin_ln_kernel<true><<<div_up_l(L, 8), 256, 0, st>>>(c.w.x, c.w.xn, sp<float>(s, p + ".norm2.weight"),
-                                                           sp<float>(s, p + ".norm2.bias"), L, C);
-      IR_CUDA_CHECK(cudaGetLastError());
-      IR_TRY(linear(c, p + ".mlp.fc1", c.w.xn, CP, (int)L, hid, CP, EPI_BF16, c.w.hid, HP, nullptr, nullptr));
-      swin_gelu_kernel<<<grid_for(L * HP), 256, 0, st>>>(c.w.hid, L, hid);
-      IR_CUDA_CHECK(cudaGetLastError());
+      IR_CUDA_CHECK(launch_pdl(swin_ln_kernel<true>, dim3(div_up_l(L, 8)), dim3(256), 0, st, (const float*)c.w.x, (void*)c.w.xn,
+                               sp<float>(s, p + ".norm2.weight"), sp<float>(s, p + ".norm2.bias"), L, C));
+      // fc1 + exact GELU in the GEMM epilogue; the pad columns [360, 384) of hid stay at their memset zero
+      IR_TRY(linear(c, p + ".mlp.fc1", c.w.xn, CP, (int)L, hid, CP, EPI_BF16_GELU, c.w.hid, HP, nullptr, nullptr));
       // x += fc2(gelu(fc1)); the last block of the group also leaves the bf16 copy the RSTB conv reads
       const bool last = bi + 1 == cfg.depth;
       IR_TRY(linear(c, p + ".mlp.fc2", c.w.hid, HP, (int)L, C, HP, EPI_F32, last ? c.w.xb : nullptr, CP, c.w.x, c.w.x));
