@@ -33,6 +33,17 @@ DIT_FLOP_1024 = 9.683e12   # SURVEY 8d, torch FlopCounter on the reference (per 
 VAE_FLOP_1024 = 10.47e12
 
 
+def _flops_per_image(side: int) -> float:
+    """linear layers / convs scale with the pixel count, the two attentions with its square."""
+    T = (side // 16) ** 2
+    P = (side // 8) ** 2
+    D, Lc, Lmax = 1152, 120, 120
+    dit = (41 * (28 * T * D * D + 4 * Lc * D * D + 4 * T * T * D + 4 * T * Lc * D) + 28 * T * D * D + 4 * T * 16 * D
+           + 2 * Lmax * (4096 * D + D * D) + 2 * T * D * 32)
+    vae = 605.5e6 * P + 4.0 * P * P * 512
+    return float(dit + vae)
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -189,9 +200,12 @@ def run_cuda(args):
     side = args.size
     _, _, y, mask, _ = weights.make_inputs(1, 8, 8, seed=9, lens=(77,))
     y, mask = y.to(dev), mask.to(dev)
-    img_u8 = weights.synthetic_degraded_image(side, side, seed=0 if args.workload == 'tiled' else rank)
-    host_img = torch.from_numpy(img_u8).pin_memory()
-    control = host_img.to(dev).float().div(255.0).permute(2, 0, 1)[None].contiguous()
+    nb = 1 if args.workload == "tiled" else max(1, args.batch)   # images per GPU and step (BASELINE configs[2], [4])
+    imgs_u8 = [weights.synthetic_degraded_image(side, side, seed=0 if args.workload == 'tiled' else rank * nb + i)
+               for i in range(nb)]
+    host_img = torch.from_numpy(np.stack(imgs_u8)).pin_memory()
+    host_list = [host_img[i].numpy() for i in range(nb)]
+    control = host_img.to(dev).float().div(255.0).permute(0, 3, 1, 2).contiguous()
     init_noise = (enc.encode(control * 2 - 1).latent_dist.mode() * 0.18215).contiguous()
     tiled = args.workload == "tiled"
 
@@ -199,7 +213,7 @@ def run_cuda(args):
         return pipeline.restore_latents(net, vae, control, init_noise, y, mask, tiled=tiled, scheduler=sched)
 
     def step_e2e():
-        preds, _ = ir.process(net, [host_img.numpy()], strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
+        preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
                               tiled=tiled, tile_size=512, tile_stride=448, vae=vae, y=y, y_mask=mask, scheduler=sched)
         return preds
 
@@ -226,7 +240,7 @@ def run_cuda(args):
             total = float(t.item())
         return total, per
 
-    mp_per_step = side * side / 1e6 * (1 if tiled else world)  # tiled: one image sharded over all ranks
+    mp_per_step = side * side / 1e6 * (1 if tiled else world * nb)  # tiled: one image sharded over all ranks
     clocks = ClockSampler(local)
     launches0 = _lib.launch_count()
     total_ms, per = timed(step_resident, args.steps, max(3, args.warmup))
@@ -238,7 +252,7 @@ def run_cuda(args):
     import zlib
     chk_img = step_resident()
     torch.cuda.synchronize()
-    checksum = zlib.crc32(pipeline.to_uint8_nhwc(chk_img).cpu().numpy().tobytes())
+    checksum = zlib.crc32(pipeline.to_uint8_nhwc(chk_img[:1]).cpu().numpy().tobytes())
 
     # one extra resident step inside a cudaProfilerStart/Stop range (outside every timed region) so that the same
     # command can be profiled with `ncu --profile-from-start off` (profiles/README.md)
@@ -265,14 +279,14 @@ def run_cuda(args):
             return vae_full.encode(x_img).latent_dist.mode()
 
         def step_e2e_native():
-            preds, _ = ir.process(net, [host_img.numpy()], strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
+            preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
                                   tiled=tiled, tile_size=512, tile_stride=448, vae=vae_full, y=y, y_mask=mask, scheduler=sched)
             return preds
 
         enc_ms, _ = timed(step_encode, args.steps, 2)
         e2e_nat_ms, _ = timed(step_e2e_native, args.steps, 1)
-        enc_flops = 4.5e12 * (side / 1024.0) ** 2   # 1.12 TFLOP per 512x512 image
-        enc_info = {"ms_per_image": enc_ms / args.steps, "tflops": enc_flops / (enc_ms / args.steps / 1e3) / 1e12,
+        enc_flops = 4.5e12 * (side / 1024.0) ** 2 * nb   # 1.12 TFLOP per 512x512 image
+        enc_info = {"ms_per_image": enc_ms / args.steps / nb, "tflops": enc_flops / (enc_ms / args.steps / 1e3) / 1e12,
                     "e2e_with_native_encoder": {"value": mp_per_step * args.steps / (e2e_nat_ms / 1e3), "unit": UNIT,
                                                 "ms_per_step": e2e_nat_ms / args.steps},
                     "note": "AutoencoderKL.encode of the whole image on the device (reference: inference.py:104-109); "
@@ -282,7 +296,7 @@ def run_cuda(args):
         # the stage-1 SwinIR on the same image
         swin = ir.SwinIR(weights.make_swinir_state_dict(seed=7), device=dev)
         swin_ms, _ = timed(lambda: swin(control), args.steps, 2)
-        enc_info["swinir_stage1"] = {"ms_per_image": swin_ms / args.steps,
+        enc_info["swinir_stage1"] = {"ms_per_image": swin_ms / args.steps / nb,
                                      "note": "SwinIR.forward (configs/swinir.yaml) of the whole image on the device"}
         del swin
         torch.cuda.empty_cache()
@@ -343,18 +357,18 @@ def run_cuda(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"one {CPU_SAMPLE}x{CPU_SAMPLE} image through the fp32 CPU port of the reference path "
                              f"(DiT+ControlNet 28+13, eps->x0, VAE decode), {sec:.1f} s, no warm-up"}
-        flops_step = (DIT_FLOP_1024 + VAE_FLOP_1024) * (side / 1024.0) ** 2 if not tiled else None
+        flops_step = _flops_per_image(side) * nb if not tiled else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (f"tiled {side}x{side} restore, tile 512/448, tiles sharded over {world} GPU(s)" if tiled else
-                                    f"one-step restore {side}x{side} b1 per GPU (BASELINE.json configs[1])"),
+                                    f"one-step restore {side}x{side} b{nb} per GPU" + (" (BASELINE.json configs[1])" if (side, nb) == (IMG, 1) else "")),
                        "model": f"random-init PixArt-XL/2 ({depth} blocks) + ControlNet-Half({cb}) + SD-VAE decoder",
                        "parallelism": f"dp{world} (images/tiles sharded, weights replicated)",
                        "l2": "no flush: the per-step working set (1.9 GB bf16 weights + activations) exceeds the 126 MB L2",
                        "caption": "120-token synthetic T5 embedding, 77 valid; caption K/V cached across steps (constant per run)"},
-            "p50_ms_per_image": statistics.median(per),
+            "p50_ms_per_image": statistics.median(per) / nb,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "api": "instarevive_b200.process(model, [uint8 HWC image], ...)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
@@ -375,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--workload", choices=["image", "tiled"], default="image")
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU and step (image workload; configs[2]/[4] sweeps)")
     ap.add_argument("--size", type=int, default=None, help="image side; default 1024 (image) / 2048 (tiled)")
     ap.add_argument("--depth", type=int, default=28)
     ap.add_argument("--copy-blocks", type=int, default=13)

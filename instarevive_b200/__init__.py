@@ -7,6 +7,7 @@ from .generate import DDPMSchedulerLite, eps_to_mu, forward_model, generate_samp
 from .nets import ControlPixArtMSHalf, PixArtMS, PixArtMS_XL_2, PixArtMSBlock  # noqa: F401
 from .pipeline import _sliding_windows, process, restore_latents  # noqa: F401
 from .swinir import SwinIR  # noqa: F401
+from .transformer_controlnet import ControlTransformerHalf, Transformer2DModel, Transformer2DModelOutput  # noqa: F401
 from .vae import AutoencoderKL, AutoencoderKLDecoder, DiagonalGaussianDistribution  # noqa: F401
 
 __version__ = "0.1.0"

@@ -9,6 +9,7 @@
 #include "vae.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace ir {
 
@@ -392,6 +393,23 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
   }
 }
 
+// conv_out on the tensor cores leaves (pixel, 4) fp32 rows (channel 3 is padding); this writes the NCHW image with the
+// caller's affine. 16 B read + 12 B written per pixel.
+__global__ void __launch_bounds__(256) nhwc4_to_nchw3_kernel(const float4* __restrict__ src, float* __restrict__ out,
+                                                             long hw, long total, float out_scale, float out_shift) {
+  pdl_wait();
+  pdl_launch();
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const float4 v = src[i];
+    const long n = i / hw, pix = i - n * hw;
+    float* o = out + n * 3 * hw + pix;
+    o[0] = v.x * out_scale + out_shift;
+    o[hw] = v.y * out_scale + out_shift;
+    o[2 * hw] = v.z * out_scale + out_shift;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ encoder helpers
 // Downsample.forward (model.py:82-89): F.pad(x, (0,1,0,1)) then a 3x3 stride-2 conv without padding. The strided
 // gather is materialised as the K-major A operand of a plain GEMM: A[(b,oy,ox)][(ky*3+kx)*C + c] = x[b][2oy+ky][2ox+kx][c]
@@ -536,8 +554,11 @@ int vae_create(const VaeConfig& cfg, Vae** out) {
     vae_add_conv(v, e + ".conv_out", 2 * cfg.z_channels, cin, 3);
     vae_add_conv(v, "quant_conv", 2 * cfg.z_channels, 2 * cfg.z_channels, 1, VP_F32);
   }
+  const size_t co_w_bytes = (size_t)4 * 9 * (cfg.ch * cfg.ch_mult[0]) * sizeof(bf16);
   if (cudaMalloc(&v->wb, (size_t)v->wb_elems * sizeof(bf16)) != cudaSuccess ||
-      cudaMalloc(&v->wf, (size_t)v->wf_elems * sizeof(float)) != cudaSuccess) {
+      cudaMalloc(&v->wf, (size_t)v->wf_elems * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&v->co_w, co_w_bytes) != cudaSuccess || cudaMalloc(&v->co_b, 4 * sizeof(float)) != cudaSuccess ||
+      cudaMemset(v->co_w, 0, co_w_bytes) != cudaSuccess || cudaMemset(v->co_b, 0, 4 * sizeof(float)) != cudaSuccess) {
     set_last_error("vae_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     vae_destroy(v);
     return IR_ERR_CUDA;
@@ -550,6 +571,8 @@ void vae_destroy(Vae* v) {
   if (!v) return;
   cudaFree(v->wb);
   cudaFree(v->wf);
+  cudaFree(v->co_w);
+  cudaFree(v->co_b);
   delete v;
 }
 
@@ -602,9 +625,13 @@ int vae_load_param(Vae* v, const char* name, const float* src, long numel, cudaS
       break;
     case VP_CONVOUT_F32:
       pack_convout_kernel<<<grid, 256, 0, s>>>(src, v->wf + p.offset, p.cout, p.cin);
+      // tensor-core path: the same 3 rows in the implicit-GEMM layout (row 3 of co_w stays zero)
+      pack_conv_bf16_kernel<<<grid, 256, 0, s>>>(src, v->co_w, p.cout, p.cin, 9);
       break;
     default:
       IR_CUDA_CHECK(cudaMemcpyAsync(v->wf + p.offset, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (p.name == "decoder.conv_out.bias")
+        IR_CUDA_CHECK(cudaMemcpyAsync(v->co_b, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   IR_CUDA_CHECK(cudaGetLastError());
   p.loaded = true;
@@ -912,6 +939,40 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
   }
   bf16* hn = c.w.buf[(cur + 1) & 3];
   IR_TRY(group_norm(c, d + ".norm_out", c.w.buf[cur], hn, H * W, C, true));
+  static const bool legacy_conv_out = [] {
+    const char* e = getenv("IR_VAE_CONVOUT_LEGACY");   // debugging aid: A/B against the CUDA-core kernel
+    return e && e[0] == '1';
+  }();
+  if (!legacy_conv_out) {
+    // conv_out (3x3, C -> 3) on the implicit-GEMM kernel: N padded to 4 (zero weight row), fp32 (pixel, 4) rows into a
+    // free activation buffer, then one pass to the NCHW image with the caller's affine
+    float* nhwc4 = reinterpret_cast<float*>(c.w.buf[(cur + 2) & 3]);
+    GemmArgs g;
+    g.A = hn;
+    g.W = v->co_w;
+    g.ldw = 9L * C;
+    g.M = B * H * W;
+    g.N = 4;
+    g.K = 9 * C;
+    g.conv = 1;
+    g.nimg = B;
+    g.H = H;
+    g.Wd = W;
+    g.C = C;
+    g.epi = EPI_F32;
+    g.bias = v->co_b;
+    g.out_f32 = nhwc4;
+    g.ldo_f = 4;
+    IR_TRY(gemm_launch(g, s));
+    const long total = (long)B * H * W;
+    int grid = div_up_l(total, 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    IR_CUDA_CHECK(launch_pdl(nhwc4_to_nchw3_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(nhwc4), out,
+                             (long)H * W, total, out_scale, out_shift));
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return IR_OK;
+  }
   IR_REQUIRE(C == 128, "vae_decode: conv_out kernel is specialised for 128 input channels (got %d)", C);
   {
     constexpr int smem = (10 * 34) * (128 + 8) * 2 + 3 * 9 * 128 * 4;

@@ -34,14 +34,36 @@ def eps_to_mu(scheduler, model_output, sample, timesteps):
     return out
 
 
+def _is_flavour_b(model) -> bool:
+    cfg = getattr(model, "config", None)
+    return cfg is not None and hasattr(cfg, "sample_size")
+
+
 def forward_model(model, latents, timestep, prompt_embeds, prompt_attention_masks=None, c=None):
-    """generate.py:54-87: micro-conditioning from the latent size, timestep expanded to the batch."""
+    """generate.py:54-87: micro-conditioning from the latent size, timestep expanded to the batch. Returns the full
+    (B,8,h,w) output; eps_to_mu keeps channels [0,4) (generate.py:84-85).
+
+    Flavour (A) models (ControlPixArtMSHalf) are called with the native signature; flavour (B) models
+    (instarevive_b200.Transformer2DModel / ControlTransformerHalf, recognised by `config.sample_size` exactly as the
+    reference does at :56) with the diffusers keywords of :66-82."""
     B, _, h, w = latents.shape
+    ts = timestep.to(latents.device).float().expand(B)
+    if _is_flavour_b(model):
+        added_cond_kwargs = {"resolution": None, "aspect_ratio": None}
+        if model.config.sample_size == 128:   # :56-62 -- note: latent height / width, as the reference passes them
+            added_cond_kwargs = {
+                "resolution": torch.tensor([float(h), float(w)], device=latents.device).repeat(B, 1),
+                "aspect_ratio": torch.tensor([float(h / w)], device=latents.device).repeat(B, 1),
+            }
+        kw = dict(timestep=ts, encoder_hidden_states=prompt_embeds, encoder_attention_mask=prompt_attention_masks,
+                  added_cond_kwargs=added_cond_kwargs)
+        if c is None:
+            return model(latents, **kw).sample
+        return model(latents, c=c, **kw)
     data_info = {
         "img_hw": torch.tensor([[float(h * 8), float(w * 8)]], device=latents.device).repeat(B, 1),
         "aspect_ratio": torch.tensor([[float(h) / float(w)]], device=latents.device).repeat(B, 1),
     }
-    ts = timestep.to(latents.device).float().expand(B)
     return model(latents, ts, prompt_embeds, mask=prompt_attention_masks, data_info=data_info, c=c)
 
 

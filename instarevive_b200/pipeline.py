@@ -166,7 +166,14 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
     h, w = height // 8, width // 8
     if not tiled:
         latents = generate_sample_1step(model, scheduler, init_noise, 400, y, y_mask)
-        img = vae.decode_tensor(latents, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
+        # big batches are decoded in chunks (bounded workspace; every image's result is independent of the batch
+        # it is decoded in, so chunking is bit-neutral)
+        chunk = max(16, decode_batch)
+        if n <= chunk:
+            img = vae.decode_tensor(latents, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
+        else:
+            img = torch.cat([vae.decode_tensor(latents[i:i + chunk], in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
+                             for i in range(0, n, chunk)], dim=0)
         return (img, latents) if return_latents else img
 
     rank, world = _dist_info(group) if distributed else (0, 1)

@@ -4,9 +4,11 @@ B200-native path. The argparse surface is the one of the reference's test_script
 follows its main() (:230-347): resize by --sr_scale, auto-resize / pad to x64, process(), crop, LANCZOS back, save PNG.
 
 What differs, by construction of the hot-path scope:
-  * the generator is ControlPixArtMSHalf on hand-written sm_100a kernels (operator surface (A)); `--ckpt` is a
-    torch.save'd state_dict with the reference's keys (base_model.* / controlnet.* or bare PixArt keys), or the literal
-    `random:<seed>` for the seeded random-init weights used in the parity tests (no checkpoint ships offline);
+  * the generator runs on hand-written sm_100a kernels; `--ckpt` is a torch.save'd state_dict -- the diffusers
+    Transformer2DModel keys of the released InstaRevive_v1.ckpt (flavour (B): instarevive_b200.Transformer2DModel /
+    ControlTransformerHalf) or the reference's PixArt keys (base_model.* / controlnet.* or bare; flavour (A):
+    ControlPixArtMSHalf) -- or the literal `random:<seed>` for the seeded random-init weights used in the parity tests
+    (no checkpoint ships offline);
   * the VAE weights come from `--vae_ckpt` (a state_dict with the AutoencoderKL keys post_quant_conv.*, decoder.*,
     encoder.*, quant_conv.*) or `random:<seed>`; encode and decode both run on the sm_100a kernels
     (instarevive_b200.AutoencoderKL). A checkpoint that holds only the decoder keys falls back to the synthetic stride-8
@@ -114,6 +116,25 @@ def _load_sd(spec: str, maker):
     return sd.get("state_dict", sd)
 
 
+def build_generator(sd):
+    """The generator class follows the checkpoint: the released `InstaRevive_v1.ckpt` is a bare diffusers
+    Transformer2DModel state dict (reference: inference.py:238-242) -> flavour (B), 28 blocks, no control branch;
+    `base_model.* / controlnet.*` checkpoints get the ControlNet-Half wrapper of their flavour (13 copied blocks,
+    pixart_controlnet.py:188 / transformer_controlnet.py:58)."""
+    from instarevive_b200 import convert
+    n_ctrl = 0
+    while f"controlnet.{n_ctrl}.after_proj.weight" in sd:
+        n_ctrl += 1
+    if convert.is_diffusers_layout(sd):
+        model = ir.Transformer2DModel(sample_size=64)
+        if n_ctrl:
+            model = ir.ControlTransformerHalf(model, n_ctrl)
+    else:
+        model = ir.ControlPixArtMSHalf(ir.PixArtMS_XL_2(input_size=64, micro_condition=True, init_weights=False), n_ctrl)
+    model.load_state_dict(sd, strict=True)
+    return model.eval()
+
+
 def main() -> None:
     args = parse_args()
     torch.manual_seed(args.seed)
@@ -122,9 +143,7 @@ def main() -> None:
         raise RuntimeError("instarevive_b200 runs on CUDA (sm_100a) only; there is no CPU/MPS path")
     dev = torch.device("cuda")
 
-    model = ir.ControlPixArtMSHalf(ir.PixArtMS_XL_2(input_size=64, micro_condition=True, init_weights=False), 13).eval()
-    model.load_state_dict(_load_sd(args.ckpt, lambda s: weights.make_dit_state_dict(28, 13, seed=s)), strict=True)
-    model = model.to(dev)
+    model = build_generator(_load_sd(args.ckpt, lambda s: weights.make_dit_state_dict(28, 13, seed=s))).to(dev)
 
     vae_sd = _load_sd(args.vae_ckpt, lambda s: weights.make_vae_state_dict(dec_seed=s))
     if any(k.startswith("encoder.") for k in vae_sd):

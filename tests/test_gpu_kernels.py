@@ -167,7 +167,9 @@ def test_attention_trace_entry_point(ctx):
     assert int(stamps[0, 0, 1]) > 0 and int(stamps[2, 0, 2]) > int(stamps[2, 0, 0]) > 0
 
 
-@pytest.mark.parametrize("B,T,lens", [(2, 1024, [120, 77]), (3, 600, [1, 300, 64]), (1, 100, [33])])
+@pytest.mark.parametrize("B,T,lens", [(2, 1024, [120, 77]), (3, 600, [1, 300, 64]), (1, 100, [33]),
+                                      # 128-row CTAs walking 2 / 4 query tiles each (K/V resident or streamed, ragged tail)
+                                      (1, 4096, [77]), (4, 4000, [120, 300, 77, 5])])
 def test_varlen_cross_attention(ctx, B, T, lens):
     _lib, L, dev = ctx
     heads, hd = 16, 72

@@ -193,3 +193,103 @@ def test_dpm_solver_schedule_and_plan_match_reference(steps):
         assert (x - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item()), f"step {i}"
     ref_end = torch.from_numpy(g["x_end_cfg1.0"]).double()
     assert (x - ref_end).abs().max().item() <= 2e-4 * ref_end.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ flavour (B) surface
+class _Recorder(torch.nn.Module):
+    """Stands in for the flavour-(A) operator: records the call the adapter makes (no CUDA needed)."""
+
+    copy_blocks_num = 0
+
+    def __init__(self):
+        super().__init__()
+        self.calls = []
+
+    def forward(self, x, ts, y, mask=None, data_info=None, c=None):
+        self.calls.append(dict(x=x, ts=ts, y=y, mask=mask, data_info=data_info, c=c))
+        return torch.zeros(x.shape[0], 8, x.shape[2], x.shape[3])
+
+
+def test_flavour_b_argument_mapping_and_return_conventions():
+    """diffusers keywords (generate.py:66-82, transformer_controlnet.py:96-173) -> native forward arguments."""
+    import instarevive_b200 as ir
+    m = ir.Transformer2DModel(sample_size=64, num_layers=1)
+    assert m.config.sample_size == 64 and m.config.out_channels == 8 and not m.use_additional_conditions
+    rec = _Recorder()
+    m.net = rec
+    lat = torch.randn(2, 4, 8, 12)
+    y = torch.randn(2, 5, 4096)
+    mask2 = torch.tensor([[1, 1, 0, 0, 0], [1, 1, 1, 1, 0]])
+    out = m(lat, timestep=torch.tensor([400, 400]), encoder_hidden_states=y, encoder_attention_mask=mask2,
+            added_cond_kwargs={"resolution": None, "aspect_ratio": None})
+    assert isinstance(out, ir.Transformer2DModelOutput) and out.sample.shape == (2, 8, 8, 12)
+    call = rec.calls[-1]
+    assert call["y"].shape == (2, 1, 5, 4096) and call["c"] is None
+    assert call["mask"].shape == (2, 1, 1, 5) and call["mask"][:, 0, 0].tolist() == mask2.tolist()
+    assert call["ts"].tolist() == [400.0, 400.0]
+    assert call["data_info"]["img_hw"].shape == (2, 2) and call["data_info"]["aspect_ratio"].shape == (2, 1)
+    # the CLI's 3-D float one/zero mask (inference.py:274-277) and flavour (A)'s 4-D mask: non-zero = valid token
+    for mk in (mask2[:, None, :].float(), mask2[:, None, None, :]):
+        m(lat, timestep=400, encoder_hidden_states=y, encoder_attention_mask=mk)
+        assert rec.calls[-1]["mask"][:, 0, 0].tolist() == mask2.tolist()
+        assert rec.calls[-1]["ts"].tolist() == [400.0, 400.0]   # scalar timestep broadcast to the batch
+    assert isinstance(m(lat, timestep=400, encoder_hidden_states=y, return_dict=False), tuple)
+    with pytest.raises(ValueError):
+        m(lat, timestep=400, encoder_hidden_states=y, encoder_attention_mask=torch.ones(2, 7))
+    with pytest.raises(TypeError):
+        m(lat, timestep=400)
+    with pytest.raises(NotImplementedError):
+        m(lat, timestep=400, encoder_hidden_states=y, class_labels=torch.zeros(2))
+
+    # the 1024 px configuration needs the micro-conditions (diffusers raises too) and passes them through unchanged
+    m128 = ir.Transformer2DModel(sample_size=128, num_layers=1)
+    assert m128.use_additional_conditions and m128.config.interpolation_scale == 2.0
+    m128.net = rec
+    with pytest.raises(ValueError):
+        m128(lat, timestep=400, encoder_hidden_states=y, added_cond_kwargs={"resolution": None, "aspect_ratio": None})
+    m128(lat, timestep=400, encoder_hidden_states=y,
+         added_cond_kwargs={"resolution": torch.tensor([[64.0, 96.0]] * 2), "aspect_ratio": torch.tensor([[0.5]] * 2)})
+    assert rec.calls[-1]["data_info"]["img_hw"].tolist() == [[64.0, 96.0]] * 2
+    assert rec.calls[-1]["data_info"]["aspect_ratio"].tolist() == [[0.5]] * 2
+
+    # ControlTransformerHalf returns the bare tensor (transformer_controlnet.py:170-173) and forwards c
+    base = ir.Transformer2DModel(sample_size=64, num_layers=2)
+    ctl = ir.ControlTransformerHalf(base, copy_blocks_num=1)
+    assert ctl.copy_blocks_num == 1 and ctl.total_blocks_num == 2
+    rec2 = _Recorder()
+    ctl.net = rec2
+    o = ctl(lat, timestep=400, encoder_hidden_states=y, c=lat)
+    assert torch.is_tensor(o) and rec2.calls[-1]["c"] is lat
+    assert isinstance(ctl(lat, timestep=400, encoder_hidden_states=y, c=lat, return_dict=False), tuple)
+
+
+def test_flavour_b_state_dict_is_diffusers_layout_and_generate_dispatch():
+    import instarevive_b200 as ir
+    from instarevive_b200 import generate
+    m = ir.Transformer2DModel(sample_size=64, num_layers=2)
+    sd = m.state_dict()
+    assert "transformer_blocks.1.attn1.to_q.weight" in sd and "adaln_single.linear.weight" in sd
+    assert not any("resolution_embedder" in k or "aspect_ratio_embedder" in k for k in sd)   # 512 px model: none
+    assert not any(k.startswith("base_model.") for k in sd)
+    m2 = ir.Transformer2DModel(sample_size=64, num_layers=2)
+    m2.load_state_dict(sd, strict=True)
+    for (k, a), (_, b) in zip(sorted(m.net.state_dict().items()), sorted(m2.net.state_dict().items())):
+        if not (k.endswith("y_embedding") or k.endswith("pos_embed")):
+            assert torch.equal(a, b), k
+    # size embedders stay zero for the 512 px model -> exact +0 on the timestep embedding
+    assert all(float(p.abs().max()) == 0.0 for p in m2.net.base_model.csize_embedder.parameters())
+    ctl = ir.ControlTransformerHalf(m2, 1)
+    assert torch.equal(ctl.net.controlnet[0].copied_block.attn.qkv.weight, m2.net.base_model.blocks[0].attn.qkv.weight)
+    assert "controlnet.0.copied_block.attn2.to_k.weight" in ctl.state_dict()
+    ctl.load_state_dict(ctl.state_dict(), strict=True)
+    ctl.load_state_dict(sd, strict=True)   # a bare transformer checkpoint loads into base_model (pixart_controlnet.py:151-163)
+    with pytest.raises(Exception):
+        ir.Transformer2DModel(sample_size=64, num_layers=2).load_state_dict({"transformer_blocks.0.scale_shift_table": sd["transformer_blocks.0.scale_shift_table"]})
+
+    # forward_model dispatches on config.sample_size the way generate.py:56 does
+    rec = _Recorder()
+    m.net = rec
+    lat = torch.randn(1, 4, 8, 8)
+    out = generate.forward_model(m, lat, torch.tensor([400]), torch.randn(1, 1, 3, 4096), torch.ones(1, 1, 1, 3))
+    assert out.shape == (1, 8, 8, 8) and rec.calls[-1]["y"].shape == (1, 1, 3, 4096)
+    assert generate._is_flavour_b(m) and not generate._is_flavour_b(rec)
