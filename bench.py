@@ -155,8 +155,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"one-step restore {IMG}x{IMG} b1 per GPU (CPU arm: bounded {CPU_SAMPLE}x{CPU_SAMPLE} sample)",
-                   "model": "random-init PixArt-XL/2 + ControlNet-Half(13) + SD-VAE decoder"},
+        "config": {"workload": f"one-step restore {IMG}x{IMG} b1 per GPU (BASELINE.json configs[1])",
+                   "model": "random-init PixArt-XL/2 (28 blocks) + ControlNet-Half(13) + SD-VAE decoder",
+                   "parallelism": "host cores of rank 0 (torch intra-op threads); other ranks idle",
+                   "sample": f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image, 1/16 of the workload's pixels (the CPU path is "
+                             "linear in pixels except for the attention terms, which favours the CPU at the smaller size)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p50_ms_per_image": 1e3 * statistics.median(times), "gpu_launches": 0,

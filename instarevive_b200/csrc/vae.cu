@@ -393,20 +393,57 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
   }
 }
 
-// conv_out on the tensor cores leaves (pixel, 4) fp32 rows (channel 3 is padding); this writes the NCHW image with the
-// caller's affine. 16 B read + 12 B written per pixel.
-__global__ void __launch_bounds__(256) nhwc4_to_nchw3_kernel(const float4* __restrict__ src, float* __restrict__ out,
-                                                             long hw, long total, float out_scale, float out_shift) {
+// conv_out on the tensor cores, without a halo: a plain GEMM over the channels gives every pixel's 27 tap responses
+// Y[pixel][tap*3 + o] = sum_c w[o][c][tap] * x[pixel][c] (the activation is read ONCE; the implicit-GEMM conv would pull
+// it through L2 three times for 3 useful output columns), and this kernel sums the 9 neighbours' responses:
+// out[o](y, x) = bias[o] + sum_tap Y[(y + ky - 1, x + kx - 1)][tap*3 + o], out-of-image neighbours contribute 0 (zero
+// padding), then the caller's affine; NCHW fp32. 32 x 8 output pixels per block, (34 x 10) x 27 responses in shared memory.
+__global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __restrict__ Y, const float* __restrict__ bias,
+                                                              float* __restrict__ out, int H, int W, float out_scale,
+                                                              float out_shift) {
+  constexpr int TW = 32, TH = 8, HW_ = TW + 2, HH_ = TH + 2, NR = 27, LDY = 32;
+  __shared__ float sm[HH_ * HW_ * NR];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   pdl_wait();
   pdl_launch();
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += stride) {
-    const float4 v = src[i];
-    const long n = i / hw, pix = i - n * hw;
-    float* o = out + n * 3 * hw + pix;
-    o[0] = v.x * out_scale + out_shift;
-    o[hw] = v.y * out_scale + out_shift;
-    o[2 * hw] = v.z * out_scale + out_shift;
+  for (int i = threadIdx.x; i < HH_ * HW_ * (LDY / 4); i += 256) {
+    const int q = i % (LDY / 4), pp = i / (LDY / 4);
+    const int yy = y0 + pp / HW_ - 1, xx = x0 + pp % HW_ - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = *reinterpret_cast<const float4*>(Y + (((long)n * H + yy) * W + xx) * LDY + q * 4);
+    float* d = sm + pp * NR + q * 4;
+    if (q * 4 + 0 < NR) d[0] = v.x;
+    if (q * 4 + 1 < NR) d[1] = v.y;
+    if (q * 4 + 2 < NR) d[2] = v.z;
+    if (q * 4 + 3 < NR) d[3] = v.w;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  const int ox = x0 + tx, oy = y0 + ty;
+  float acc[3] = {bias[0], bias[1], bias[2]};
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* r = sm + ((ty + tap / 3) * HW_ + tx + tap % 3) * NR + tap * 3;   // stride 27 floats: conflict-free
+    acc[0] += r[0];
+    acc[1] += r[1];
+    acc[2] += r[2];
+  }
+  if (ox < W && oy < H) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) out[(((long)n * 3 + o) * H + oy) * W + ox] = acc[o] * out_scale + out_shift;
+  }
+}
+
+// (3, Cin, 3, 3) fp32 -> [tap*3 + o][c] bf16 (conv_out as a tap-response GEMM; rows 27..31 of the buffer stay zero)
+__global__ void pack_convout_taps_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int cout, int cin) {
+  const long total = (long)cout * cin * 9;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int o = (int)((i / cin) % cout);
+    const int tap = (int)(i / ((long)cin * cout));
+    dst[i] = __float2bfloat16(src[((long)o * cin + c) * 9 + tap]);
   }
 }
 
@@ -554,7 +591,7 @@ int vae_create(const VaeConfig& cfg, Vae** out) {
     vae_add_conv(v, e + ".conv_out", 2 * cfg.z_channels, cin, 3);
     vae_add_conv(v, "quant_conv", 2 * cfg.z_channels, 2 * cfg.z_channels, 1, VP_F32);
   }
-  const size_t co_w_bytes = (size_t)4 * 9 * (cfg.ch * cfg.ch_mult[0]) * sizeof(bf16);
+  const size_t co_w_bytes = (size_t)32 * (cfg.ch * cfg.ch_mult[0]) * sizeof(bf16);   // 27 tap-response rows + 5 zero rows
   if (cudaMalloc(&v->wb, (size_t)v->wb_elems * sizeof(bf16)) != cudaSuccess ||
       cudaMalloc(&v->wf, (size_t)v->wf_elems * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&v->co_w, co_w_bytes) != cudaSuccess || cudaMalloc(&v->co_b, 4 * sizeof(float)) != cudaSuccess ||
@@ -625,8 +662,8 @@ int vae_load_param(Vae* v, const char* name, const float* src, long numel, cudaS
       break;
     case VP_CONVOUT_F32:
       pack_convout_kernel<<<grid, 256, 0, s>>>(src, v->wf + p.offset, p.cout, p.cin);
-      // tensor-core path: the same 3 rows in the implicit-GEMM layout (row 3 of co_w stays zero)
-      pack_conv_bf16_kernel<<<grid, 256, 0, s>>>(src, v->co_w, p.cout, p.cin, 9);
+      // tensor-core path: 27 tap-response rows [tap*3 + o][c]
+      pack_convout_taps_kernel<<<grid, 256, 0, s>>>(src, v->co_w, p.cout, p.cin);
       break;
     default:
       IR_CUDA_CHECK(cudaMemcpyAsync(v->wf + p.offset, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -944,31 +981,24 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
     return e && e[0] == '1';
   }();
   if (!legacy_conv_out) {
-    // conv_out (3x3, C -> 3) on the implicit-GEMM kernel: N padded to 4 (zero weight row), fp32 (pixel, 4) rows into a
-    // free activation buffer, then one pass to the NCHW image with the caller's affine
-    float* nhwc4 = reinterpret_cast<float*>(c.w.buf[(cur + 2) & 3]);
+    // conv_out (3x3, C -> 3) as a tap-response GEMM (M = pixels, N = 27 -> 32, K = C; fp32 rows into a free activation
+    // buffer) + a 9-neighbour gather-sum that writes the NCHW image with the caller's affine
+    IR_REQUIRE(v->cfg.out_ch == 3, "vae_decode: 3 output channels expected");
+    float* Y = reinterpret_cast<float*>(c.w.buf[(cur + 2) & 3]);
     GemmArgs g;
     g.A = hn;
+    g.lda = C;
     g.W = v->co_w;
-    g.ldw = 9L * C;
+    g.ldw = C;
     g.M = B * H * W;
-    g.N = 4;
-    g.K = 9 * C;
-    g.conv = 1;
-    g.nimg = B;
-    g.H = H;
-    g.Wd = W;
-    g.C = C;
+    g.N = 32;
+    g.K = C;
     g.epi = EPI_F32;
-    g.bias = v->co_b;
-    g.out_f32 = nhwc4;
-    g.ldo_f = 4;
+    g.out_f32 = Y;
+    g.ldo_f = 32;
     IR_TRY(gemm_launch(g, s));
-    const long total = (long)B * H * W;
-    int grid = div_up_l(total, 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    IR_CUDA_CHECK(launch_pdl(nhwc4_to_nchw3_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(nhwc4), out,
-                             (long)H * W, total, out_scale, out_shift));
+    IR_CUDA_CHECK(launch_pdl(conv_out_gather_kernel, dim3(div_up_l(W, 32), div_up_l(H, 8), B), dim3(256), 0, s,
+                             (const float*)Y, (const float*)v->co_b, out, H, W, out_scale, out_shift));
     IR_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return IR_OK;

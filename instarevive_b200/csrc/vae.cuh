@@ -37,7 +37,7 @@ struct Vae {
   float* wf = nullptr;
   long wb_elems = 0, wf_elems = 0;
   int first_encoder_param = -1;   // params[first_encoder_param..] belong to the encoder (decode does not need them)
-  // decoder.conv_out as an implicit GEMM: (4, 9*C) bf16 weight rows (row 3 zero) and a 4-entry bias
+  // decoder.conv_out as a tap-response GEMM: (32, C) bf16 weight rows [tap*3 + o][c] (rows 27..31 zero) and the bias
   bf16* co_w = nullptr;
   float* co_b = nullptr;
 };
