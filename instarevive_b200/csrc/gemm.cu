@@ -59,6 +59,9 @@ struct GemmDev {
   int num_tiles;
   // conv geometry
   int H, Wd, tiles_x, c_blocks;
+  int ntap, off_y, off_x;          // taps per axis (3 or 2), halo origin offset
+  int o_scale, o_oy, o_ox, oH, oW; // output pixel mapping (phase of an upsample-folded conv)
+  int gn_slot_off, gn_slots_img;
   // epilogue
   float alpha;
   const float* bias;
@@ -165,27 +168,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) {
+          // conv: one halo box + ntap weight tiles per stage (ntap = 3, or 2 for an upsample-folded phase conv)
+          const uint32_t stage_tx = CONV ? (uint32_t)(Cfg::A_BYTES + p.ntap * Cfg::B_TAP_BYTES)
+                                         : (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES);
           if (CG == 2) {
             if (cta_rank == 0)
-              mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
             else
               mbar_arrive_cluster(&full_bar[stage], 0);
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           }
           if (CONV) {
-            // stage kb = (channel chunk cb, kx): one halo box + the three ky weight tiles
-            const int cb = kb / 3;
-            const int kx = kb - cb * 3;
+            // stage kb = (channel chunk cb, kx): one halo box + the ky weight tiles
+            const int cb = kb / p.ntap;
+            const int kx = kb - cb * p.ntap;
             if (CG == 2)
-              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx - 1,
-                              ty * CONV_BH - 1, b);
+              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx + p.off_x,
+                              ty * CONV_BH + p.off_y, b);
             else
-              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx - 1,
-                          ty * CONV_BH - 1, b);
+              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, tx * CONV_BW + kx + p.off_x,
+                          ty * CONV_BH + p.off_y, b);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-              const int kcol = ((ky * 3 + kx) * p.c_blocks + cb) * BK;
+              if (ky >= p.ntap) break;
+              const int kcol = ((ky * p.ntap + kx) * p.c_blocks + cb) * BK;
               if (CG == 2)
                 tma_load_3d_2sm(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
               else
@@ -226,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          constexpr int TAPS = CONV ? 3 : 1;
+          const int TAPS = CONV ? p.ntap : 1;
           if (CG == 1 && p.dbg_nomma) {
             if (leader) {
               mbar_arrive(&empty_bar[stage]);
@@ -241,7 +248,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (leader) {
 #pragma unroll
-          for (int ky = 0; ky < TAPS; ++ky) {
+          for (int ky = 0; ky < (CONV ? 3 : 1); ++ky) {
+            if (ky >= TAPS) break;
             // conv: tap ky reads rows [16*ky, 16*ky + 128) of the halo box (+2048 B keeps the 1024 B swizzle phase)
             const uint64_t da = make_smem_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES + ky * (CONV_BW * BK * 2)));
             const uint64_t db = make_smem_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES));
@@ -310,7 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CONV) {
           const int ty = m_blk / p.tiles_x, tx = m_blk - ty * p.tiles_x;
           const int y = ty * CONV_BH + (r >> 4), x = tx * CONV_BW + (r & 15);
-          row_off[i] = (y < p.H && x < p.Wd) ? ((long)b * p.H + y) * p.Wd + x : -1;
+          row_off[i] = (y < p.H && x < p.Wd)
+                           ? ((long)b * p.oH + y * p.o_scale + p.o_oy) * p.oW + x * p.o_scale + p.o_ox : -1;
           gate_row[i] = 0;
         } else {
           const int gm = m_blk * BM + r;
@@ -586,7 +595,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 s_ += a0;
                 q_ += a1;
               }
-              const long slot = (long)img * tiles_per_img + tile_in_img;
+              const long slot = (long)img * (CONV && p.gn_slots_img ? p.gn_slots_img : tiles_per_img) +
+                                (CONV ? p.gn_slot_off : 0) + tile_in_img;
               *reinterpret_cast<float2*>(p.gn_partial + (slot * 32 + gcol / p.gn_cpg) * 2) = make_float2(s_, q_);
             }
           }
@@ -829,7 +839,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   long m_blocks_total;
   if (a.conv) {
     IR_REQUIRE(a.C % BK == 0, "conv: C=%d must be a multiple of %d", a.C, BK);
-    IR_REQUIRE(a.K == 9 * a.C, "conv: K=%d must equal 9*C=%d", a.K, 9 * a.C);
+    IR_REQUIRE(a.conv_taps == 3 || a.conv_taps == 2, "conv: %d taps per axis unsupported", a.conv_taps);
+    IR_REQUIRE(a.K == a.conv_taps * a.conv_taps * a.C, "conv: K=%d must equal taps^2*C=%d", a.K, a.conv_taps * a.conv_taps * a.C);
+    IR_REQUIRE(a.o_scale >= 1 && a.o_oy >= 0 && a.o_oy < a.o_scale && a.o_ox >= 0 && a.o_ox < a.o_scale, "conv: bad output mapping");
     IR_REQUIRE(a.M == a.nimg * a.H * a.Wd, "conv: M mismatch");
     IR_REQUIRE(a.batch == 1, "conv: batch must be 1 (images are folded into M)");
     p.H = a.H;
@@ -839,7 +851,17 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.m_blocks = p.tiles_x * tiles_y;
     p.batch = a.nimg;  // one "batch" entry per image
     p.c_blocks = a.C / BK;
-    p.k_blocks = 3 * p.c_blocks;   // pipeline steps: (channel chunk, kx), three ky taps each
+    p.ntap = a.conv_taps;
+    p.off_y = a.conv_off_y;
+    p.off_x = a.conv_off_x;
+    p.o_scale = a.o_scale;
+    p.o_oy = a.o_oy;
+    p.o_ox = a.o_ox;
+    p.oH = a.H * a.o_scale;
+    p.oW = a.Wd * a.o_scale;
+    p.gn_slot_off = a.gn_slot_off;
+    p.gn_slots_img = a.gn_slots_img;
+    p.k_blocks = p.ntap * p.c_blocks;   // pipeline steps: (channel chunk, kx), ntap ky taps each
     // the conv epilogue indexes the output by pixel; batch strides are folded into the pixel index
     p.stride_ob = 0;
     p.stride_of = 0;
@@ -862,7 +884,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
   const long m_pairs = (p.m_blocks + 1) / 2;
-  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.conv ? 3 * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
+  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.conv ? p.ntap * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
   if (a.conv && tc.cg == 1 && tc.bn == 256) tc.bn = 128;
   const int bn = tc.bn;
   p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;

@@ -62,6 +62,15 @@ struct GemmArgs {
   bf16* vt_heads = nullptr;
   int qkv_T = 0, qkv_Tp = 0, qkv_H = 0, qkv_hd = 0;
 
+  // conv only. conv_taps: taps per axis (3 = 3x3, pad 1; 2 = one phase of "nearest x2 upsample + 3x3 conv" folded into a
+  // 2x2 conv on the low-resolution input, K = 4*C). conv_off_*: halo origin (source pixel = output pixel + off + tap).
+  // Output pixel (y, x) is stored at (y * o_scale + o_oy, x * o_scale + o_ox) of an (H * o_scale) x (Wd * o_scale) image.
+  int conv_taps = 3;
+  int conv_off_y = -1, conv_off_x = -1;
+  int o_scale = 1, o_oy = 0, o_ox = 0;
+  // fused GroupNorm statistics of a conv: partial slot = img * gn_slots_img + gn_slot_off + tile (0 = tiles per image)
+  int gn_slot_off = 0, gn_slots_img = 0;
+
   int force_bn = 0;  // 0 = heuristic; 64 / 128 / 256 = single-CTA tile width; cg*1000 + bn forces (cta_group, width)
 };
 

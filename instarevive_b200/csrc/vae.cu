@@ -436,6 +436,33 @@ __global__ void __launch_bounds__(256) conv_out_gather_kernel(const float* __res
   }
 }
 
+// Upsample.forward (model.py:63-67) = nearest x2 + 3x3 conv. On the low-resolution input s that is, per output phase
+// (a, b) = (Y & 1, X & 1), a 2x2 conv: out(2y+a, 2x+b) = sum_{t,u} W_ab[t][u] . s(y + a - 1 + t, x + b - 1 + u), where
+// W_ab[t][u] sums the 3x3 taps that land on the same source pixel: rows {0 | 1,2} for a = 0 and {0,1 | 2} for a = 1 (same
+// for columns) -- 4/9 of the FLOPs, no upsampled tensor. Zero padding carries over: the out-of-image taps of the 3x3 conv
+// are exactly the out-of-image source pixels of the 2x2 one.
+// (Cout, Cin, 3, 3) fp32 -> [phase = 2a + b][Cout][t][u][Cin] bf16 (sums in fp32, one rounding)
+__global__ void pack_upconv_phases_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int cout, int cin) {
+  const long per_phase = (long)cout * 4 * cin;
+  const long total = 4 * per_phase;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cin);
+    const int u = (int)((i / cin) % 2);
+    const int t = (int)((i / (2L * cin)) % 2);
+    const int o = (int)((i / (4L * cin)) % cout);
+    const int phase = (int)(i / per_phase);
+    const int a = phase >> 1, b = phase & 1;
+    // taps of the 3x3 kernel that fall on source offset t (rows) / u (columns)
+    const int ky0 = a == 0 ? (t == 0 ? 0 : 1) : (t == 0 ? 0 : 2), ky1 = a == 0 ? (t == 0 ? 0 : 2) : (t == 0 ? 1 : 2);
+    const int kx0 = b == 0 ? (u == 0 ? 0 : 1) : (u == 0 ? 0 : 2), kx1 = b == 0 ? (u == 0 ? 0 : 2) : (u == 0 ? 1 : 2);
+    const float* w = src + ((long)o * cin + c) * 9;
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
+    dst[i] = __float2bfloat16(acc);
+  }
+}
+
 // (3, Cin, 3, 3) fp32 -> [tap*3 + o][c] bf16 (conv_out as a tap-response GEMM; rows 27..31 of the buffer stay zero)
 __global__ void pack_convout_taps_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int cout, int cin) {
   const long total = (long)cout * cin * 9;
@@ -559,7 +586,17 @@ int vae_create(const VaeConfig& cfg, Vae** out) {
       vae_add_res(v, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), block_in, block_out);
       block_in = block_out;
     }
-    if (lvl != 0) vae_add_conv(v, d + ".up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3);
+    if (lvl != 0) {
+      const std::string un = d + ".up." + std::to_string(lvl) + ".upsample.conv";
+      vae_add_conv(v, un, block_in, block_in, 3);
+      bf16* pw = nullptr;
+      if (cudaMalloc(&pw, (size_t)16 * block_in * block_in * sizeof(bf16)) != cudaSuccess) {
+        set_last_error("vae_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        vae_destroy(v);
+        return IR_ERR_CUDA;
+      }
+      v->up_w[un + ".weight"] = pw;
+    }
   }
   vae_add_norm(v, d + ".norm_out", block_in);
   vae_add_conv(v, d + ".conv_out", cfg.out_ch, block_in, 3, VP_CONVOUT_F32);
@@ -610,6 +647,7 @@ void vae_destroy(Vae* v) {
   cudaFree(v->wf);
   cudaFree(v->co_w);
   cudaFree(v->co_b);
+  for (auto& kv : v->up_w) cudaFree(kv.second);
   delete v;
 }
 
@@ -654,9 +692,13 @@ int vae_load_param(Vae* v, const char* name, const float* src, long numel, cudaS
   IR_REQUIRE(numel == p.numel, "vae_load_param: '%s' has %ld elements, expected %ld", name, numel, p.numel);
   const int grid = div_up_l(numel, 256);
   switch (p.kind) {
-    case VP_CONV_BF16:
+    case VP_CONV_BF16: {
       pack_conv_bf16_kernel<<<grid, 256, 0, s>>>(src, v->wb + p.offset, p.cout, p.cin, p.k * p.k);
+      auto up = v->up_w.find(name);
+      if (up != v->up_w.end())
+        pack_upconv_phases_kernel<<<div_up_l(16L * p.cout * p.cin, 256), 256, 0, s>>>(src, up->second, p.cout, p.cin);
       break;
+    }
     case VP_CONVIN_F32:
       pack_convin_kernel<<<grid, 256, 0, s>>>(src, v->wf + p.offset, p.cout, p.cin);
       break;
@@ -826,6 +868,50 @@ static int conv3x3(VCtx& c, const std::string& name, const bf16* x, bf16* y, con
   return IR_OK;
 }
 
+// Upsample.forward (model.py:63-67): nearest x2 + 3x3 conv as four phase 2x2 convs on the low-resolution input
+// (pack_upconv_phases_kernel). x: (B, H, W, C) -> y: (B, 2H, 2W, C); the output feeds a GroupNorm, whose statistics are
+// accumulated in the four epilogues (one partial slot per (phase, tile)).
+static int upsample_conv(VCtx& c, const std::string& name, const bf16* x, bf16* y, int H, int W, int C) {
+  auto up = c.v->up_w.find(name + ".weight");
+  IR_REQUIRE(up != c.v->up_w.end(), "upsample_conv: no phase weights for '%s'", name.c_str());
+  const int tiles = gemm_conv_tiles_per_image(H, W);
+  const bool fuse = fused_stats_ok(C) && (long)c.B * 4 * tiles * 64 <= c.w.partial_elems;
+  for (int phase = 0; phase < 4; ++phase) {
+    const int a = phase >> 1, b = phase & 1;
+    GemmArgs g;
+    g.A = x;
+    g.W = up->second + (long)phase * C * 4 * C;
+    g.ldw = 4L * C;
+    g.M = c.B * H * W;
+    g.N = C;
+    g.K = 4 * C;
+    g.conv = 1;
+    g.conv_taps = 2;
+    g.conv_off_y = a - 1;
+    g.conv_off_x = b - 1;
+    g.o_scale = 2;
+    g.o_oy = a;
+    g.o_ox = b;
+    g.nimg = c.B;
+    g.H = H;
+    g.Wd = W;
+    g.C = C;
+    g.epi = EPI_BF16;
+    g.bias = vp<float>(c.v, name + ".bias");
+    g.out_bf16 = y;
+    g.ldo_b = C;
+    if (fuse) {
+      g.gn_partial = c.w.partial;
+      g.gn_cpg = C / 32;
+      g.gn_slot_off = phase * tiles;
+      g.gn_slots_img = 4 * tiles;
+    }
+    IR_TRY(gemm_launch(g, c.s));
+  }
+  if (fuse) IR_TRY(finish_fused_stats(c, 4 * H * W, C, 4 * tiles));
+  return IR_OK;
+}
+
 static int conv1x1(VCtx& c, const bf16* wgt, const float* bias, const bf16* x, bf16* y, const bf16* resid, long M,
                    int Cin, int Cout, int stats_P = 0) {
   GemmArgs g;
@@ -959,7 +1045,16 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
       IR_TRY(res_block(c, d + ".up." + std::to_string(lvl) + ".block." + std::to_string(b), cur, H, W, C, Cout, feeds_norm));
       C = Cout;
     }
-    if (lvl != 0) {
+    static const bool legacy_upconv = [] {
+      const char* e = getenv("IR_VAE_UPCONV_LEGACY");   // debugging aid: A/B against upsample2x + 3x3 conv
+      return e && e[0] == '1';
+    }();
+    if (lvl != 0 && !legacy_upconv) {
+      IR_TRY(upsample_conv(c, d + ".up." + std::to_string(lvl) + ".upsample.conv", c.w.buf[cur], c.w.buf[(cur + 2) & 3], H, W, C));
+      H *= 2;
+      W *= 2;
+      cur = (cur + 2) & 3;
+    } else if (lvl != 0) {
       bf16* up = c.w.buf[(cur + 1) & 3];
       const long total_vec = (long)B * H * W * C / 8;   // input vectors
       int grid = div_up_l(total_vec, 256);
