@@ -180,6 +180,11 @@ int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, 
 int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
                     void* out_bf16, float* out_f32, const void* resid_bf16, const float* resid_f32, int force_bn,
                     void* stream);
+/* Upsample.forward (ldm/modules/diffusionmodules/model.py:63-67): nearest x2 + 3x3 conv (C -> C) as four 2x2 phase convs
+ * on the low-resolution input. act (n,H,W,C) NHWC bf16, weight_oihw (C,C,3,3) fp32 in the reference layout, phase_w_ws:
+ * 16*C*C bf16 scratch for the pre-summed phase weights, out (n,2H,2W,C) NHWC bf16. */
+int ir_upsample_conv3x3_bf16(const void* act, const float* weight_oihw, const float* bias, int n, int H, int W, int C,
+                             void* phase_w_ws, void* out_bf16, int force_bn, void* stream);
 int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldk,
                       long long ldv, long long ldo, int B, int heads, int head_dim, int Tq, int Tk,
                       const int32_t* kv_off, const int32_t* kv_len, float scale, void* stream);

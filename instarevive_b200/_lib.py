@@ -44,6 +44,7 @@ PROTOTYPES = {
     "ir_eps_to_x0": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "ir_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ir_conv3x3_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "ir_upsample_conv3x3_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "ir_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp]),
     "ir_gemm_qkv_heads": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "ir_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp]),

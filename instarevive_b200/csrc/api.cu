@@ -421,6 +421,17 @@ int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int 
   return gemm_launch(g, (cudaStream_t)stream);
 }
 
+int ir_upsample_conv3x3_bf16(const void* act, const float* weight_oihw, const float* bias, int n, int H, int W, int C,
+                             void* phase_w_ws, void* out_bf16, int force_bn, void* stream) {
+  if (!act || !weight_oihw || !phase_w_ws || !out_bf16) {
+    set_last_error("ir_upsample_conv3x3_bf16: null pointer");
+    return IR_ERR_INVALID;
+  }
+  IR_TRY(pack_upconv_phases(weight_oihw, (bf16*)phase_w_ws, C, C, (cudaStream_t)stream));
+  return upsample_conv_phases_launch((const bf16*)act, (const bf16*)phase_w_ws, bias, (bf16*)out_bf16, n, H, W, C, nullptr,
+                                     force_bn, (cudaStream_t)stream);
+}
+
 int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldk,
                       long long ldv, long long ldo, int B, int heads, int head_dim, int Tq, int Tk,
                       const int32_t* kv_off, const int32_t* kv_len, float scale, void* stream) {

@@ -682,6 +682,52 @@ __global__ void pack_convout_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+int pack_upconv_phases(const float* w_oihw, bf16* phase_w, int cout, int cin, cudaStream_t s) {
+  pack_upconv_phases_kernel<<<(int)((16L * cout * cin + 255) / 256), 256, 0, s>>>(w_oihw, phase_w, cout, cin);
+  IR_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return IR_OK;
+}
+
+int upsample_conv_phases_launch(const bf16* x, const bf16* phase_w, const float* bias, bf16* y, int n, int H, int W, int C,
+                                float* gn_partial, int force_bn, cudaStream_t s) {
+  const int tiles = gemm_conv_tiles_per_image(H, W);
+  for (int phase = 0; phase < 4; ++phase) {
+    const int a = phase >> 1, b = phase & 1;
+    GemmArgs g;
+    g.A = x;
+    g.W = phase_w + (long)phase * C * 4 * C;
+    g.ldw = 4L * C;
+    g.M = n * H * W;
+    g.N = C;
+    g.K = 4 * C;
+    g.conv = 1;
+    g.conv_taps = 2;
+    g.conv_off_y = a - 1;
+    g.conv_off_x = b - 1;
+    g.o_scale = 2;
+    g.o_oy = a;
+    g.o_ox = b;
+    g.nimg = n;
+    g.H = H;
+    g.Wd = W;
+    g.C = C;
+    g.epi = EPI_BF16;
+    g.bias = bias;
+    g.out_bf16 = y;
+    g.ldo_b = C;
+    g.force_bn = force_bn;
+    if (gn_partial) {
+      g.gn_partial = gn_partial;
+      g.gn_cpg = C / 32;
+      g.gn_slot_off = phase * tiles;
+      g.gn_slots_img = 4 * tiles;
+    }
+    IR_TRY(gemm_launch(g, s));
+  }
+  return IR_OK;
+}
+
 int vae_load_param(Vae* v, const char* name, const float* src, long numel, cudaStream_t s) {
   auto it = v->index.find(name);
   if (it == v->index.end()) {
@@ -876,38 +922,8 @@ static int upsample_conv(VCtx& c, const std::string& name, const bf16* x, bf16* 
   IR_REQUIRE(up != c.v->up_w.end(), "upsample_conv: no phase weights for '%s'", name.c_str());
   const int tiles = gemm_conv_tiles_per_image(H, W);
   const bool fuse = fused_stats_ok(C) && (long)c.B * 4 * tiles * 64 <= c.w.partial_elems;
-  for (int phase = 0; phase < 4; ++phase) {
-    const int a = phase >> 1, b = phase & 1;
-    GemmArgs g;
-    g.A = x;
-    g.W = up->second + (long)phase * C * 4 * C;
-    g.ldw = 4L * C;
-    g.M = c.B * H * W;
-    g.N = C;
-    g.K = 4 * C;
-    g.conv = 1;
-    g.conv_taps = 2;
-    g.conv_off_y = a - 1;
-    g.conv_off_x = b - 1;
-    g.o_scale = 2;
-    g.o_oy = a;
-    g.o_ox = b;
-    g.nimg = c.B;
-    g.H = H;
-    g.Wd = W;
-    g.C = C;
-    g.epi = EPI_BF16;
-    g.bias = vp<float>(c.v, name + ".bias");
-    g.out_bf16 = y;
-    g.ldo_b = C;
-    if (fuse) {
-      g.gn_partial = c.w.partial;
-      g.gn_cpg = C / 32;
-      g.gn_slot_off = phase * tiles;
-      g.gn_slots_img = 4 * tiles;
-    }
-    IR_TRY(gemm_launch(g, c.s));
-  }
+  IR_TRY(upsample_conv_phases_launch(x, up->second, vp<float>(c.v, name + ".bias"), y, c.B, H, W, C,
+                                     fuse ? c.w.partial : nullptr, 0, c.s));
   if (fuse) IR_TRY(finish_fused_stats(c, 4 * H * W, C, 4 * tiles));
   return IR_OK;
 }

@@ -57,4 +57,12 @@ size_t vae_encode_workspace_bytes(const Vae* v, int B, int H, int W);
 int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
                cudaStream_t s);
 
+// Upsample.forward (model.py:63-67), nearest x2 + 3x3 conv, as four 2x2 phase convs on the low-resolution input:
+// pack_upconv_phases sums the (Cout, Cin, 3, 3) fp32 taps into [phase][Cout][2][2][Cin] bf16 (16*Cout*Cin elements);
+// the launcher maps x (n,H,W,C) NHWC bf16 to y (n,2H,2W,C). gn_partial (optional): fused GroupNorm partials,
+// 4 * gemm_conv_tiles_per_image(H, W) slots of 64 floats per image.
+int pack_upconv_phases(const float* w_oihw, bf16* phase_w, int cout, int cin, cudaStream_t s);
+int upsample_conv_phases_launch(const bf16* x, const bf16* phase_w, const float* bias, bf16* y, int n, int H, int W, int C,
+                                float* gn_partial, int force_bn, cudaStream_t s);
+
 }  // namespace ir

@@ -93,6 +93,36 @@ def test_conv3x3_implicit_gemm(ctx, cfg, n, H, W, C, Co):
     _close(out.permute(0, 3, 1, 2), ref, 1e-2)
 
 
+@pytest.mark.parametrize("cfg", [64, 128, 2128, 2256])
+@pytest.mark.parametrize("n,H,W,C", [(1, 32, 32, 128), (2, 24, 40, 256), (1, 20, 36, 512)])
+def test_upsample_conv_as_phase_convs(ctx, cfg, n, H, W, C):
+    """Upsample.forward (model.py:63-67): nearest x2 + 3x3 conv, computed as four 2x2 phase convs on the low-resolution
+    input with pre-summed weights. Exact algebra; the only difference is one bf16 rounding of each summed weight."""
+    _lib, L, dev = ctx
+    g = torch.Generator().manual_seed(H + W + C)
+    x = torch.randn(n, C, H, W, generator=g).to(dev).bfloat16()
+    w = (torch.randn(C, C, 3, 3, generator=g) * 0.03).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    act = x.permute(0, 2, 3, 1).contiguous()
+    ws = torch.empty(16 * C * C, device=dev, dtype=torch.bfloat16)
+    out = torch.full((n, 2 * H, 2 * W, C), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_upsample_conv3x3_bf16(act.data_ptr(), w.data_ptr(), b.data_ptr(), n, H, W, C, ws.data_ptr(),
+                                          out.data_ptr(), cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    _close(out.permute(0, 3, 1, 2), ref, 1e-2)
+    # phase weights: [2a+b][Cout][t][u][Cin] must be the fp32 sums of the taps that share a source pixel
+    pw = ws.view(4, C, 2, 2, C).float()
+    wf = w.permute(0, 2, 3, 1)   # (Cout, ky, kx, Cin)
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    for a in (0, 1):
+        for bb in (0, 1):
+            for t in (0, 1):
+                for u in (0, 1):
+                    want = wf[:, rows[a][t]][:, :, rows[bb][u]].sum(dim=(1, 2))
+                    assert (pw[2 * a + bb, :, t, u] - want).abs().max().item() <= 2e-3   # one bf16 rounding of |w| <~ 0.4
+
+
 @pytest.mark.parametrize("B,T", [(1, 256), (2, 1000), (1, 4096), (3, 1296), (1, 72)])
 def test_qkv_heads_and_tcgen05_attention(ctx, B, T):
     _lib, L, dev = ctx
