@@ -16,9 +16,14 @@ full() {  # name, kernel regex, launch-skip, launch-count
     -k regex:"$2" --launch-skip $3 --launch-count $4 -o $OUT/full_${TAG}_$1 -f $CMD > $OUT/prof_${TAG}_ncu_$1.log 2>&1
   echo "set full $1 rc=$?"
 }
-full attn 'attn_tc_kernel' 20 2
-full gemm 'gemm_tc_kernel' 120 12
-full conv 'gemm_tc_kernel' 280 8
-full gn 'gn_apply_kernel' 22 6
-full ln 'ln_modulate_kernel|flash_attn_kernel' 40 4
+# gpurun copies back at most 64 MiB: ~2.5 MB per captured launch, so keep the captures to ~22 launches in total
+full attn 'attn_tc_kernel' 20 1
+full gemm 'gemm_tc_kernel' 120 6                           # one DiT block: qkv, proj, q_linear, cross proj, fc1, fc2
+full conv 'gemm_tc_kernel' 282 6                           # two 3x3 convs of up.2 + the four phase convs of its upsample
+full tail 'gemm_tc_kernel|conv_out_gather_kernel' 304 4    # last full-resolution convs, conv_out tap GEMM + gather
+full ln 'ln_modulate_kernel|flash_attn_kernel' 40 3
+full gn 'gn_apply_kernel' 22 2
+if [ "$(du -sm $OUT | cut -f1)" -gt 60 ]; then rm -f $OUT/full_${TAG}_gn.ncu-rep; fi
+if [ "$(du -sm $OUT | cut -f1)" -gt 60 ]; then rm -f $OUT/full_${TAG}_ln.ncu-rep; fi
+du -sm $OUT
 ls -la $OUT/full_${TAG}_*.ncu-rep $OUT/launches_${TAG}.csv
