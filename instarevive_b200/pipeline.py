@@ -196,8 +196,12 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
     noise_buffer = tile_blend(x0, coords, h, w, 1)                                    # inference.py:133-136
     # loop 2 (inference.py:139-152): decode + colour-fix my tiles, blend in pixel space
     outs = []
-    for b0 in range(s, e, max(1, decode_batch)):
-        b1 = min(e, b0 + max(1, decode_batch))
+    # balanced decode chunks of at most decode_batch tiles (25 tiles -> 7+6+6+6 rather than 8+8+8+1: a lone tile would
+    # run the decoder in its small-M regime); per-tile results do not depend on the chunking (bit-identical)
+    n_mine, cap = e - s, max(1, decode_batch)
+    n_chunks = (n_mine + cap - 1) // cap
+    bounds = [s + shard_range(n_mine, i, n_chunks)[0] for i in range(n_chunks)] + [e]
+    for b0, b1 in zip(bounds[:-1], bounds[1:]):
         cc = coords[b0:b1].contiguous()
         zt = tile_gather(noise_buffer, cc, th, tw, 1).view(-1, 4, th, tw)
         ti = vae.decode_tensor(zt, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)   # (k*N,3,8th,8tw)
