@@ -156,7 +156,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"one-step restore {IMG}x{IMG} b1 per GPU (BASELINE.json configs[1])",
-                   "model": "random-init PixArt-XL/2 (28 blocks) + ControlNet-Half(13) + SD-VAE decoder",
+                   "network": "random-init PixArt-XL/2 (28 blocks) + ControlNet-Half(13) + SD-VAE decoder",
                    "parallelism": "host cores of rank 0 (torch intra-op threads); other ranks idle",
                    "sample": f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image, 1/16 of the workload's pixels (the CPU path is "
                              "linear in pixels except for the attention terms, which favours the CPU at the smaller size)"},
@@ -370,7 +370,7 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (f"tiled {side}x{side} restore, tile 512/448, tiles sharded over {world} GPU(s)" if tiled else
                                     f"one-step restore {side}x{side} b{nb} per GPU" + (" (BASELINE.json configs[1])" if (side, nb) == (IMG, 1) else "")),
-                       "model": f"random-init PixArt-XL/2 ({depth} blocks) + ControlNet-Half({cb}) + SD-VAE decoder",
+                       "network": f"random-init PixArt-XL/2 ({depth} blocks) + ControlNet-Half({cb}) + SD-VAE decoder",
                        "parallelism": f"dp{world} (images/tiles sharded, weights replicated)",
                        "l2": "no flush: the per-step working set (1.9 GB bf16 weights + activations) exceeds the 126 MB L2",
                        "caption": "120-token synthetic T5 embedding, 77 valid; caption K/V cached across steps (constant per run)"},
