@@ -62,6 +62,8 @@ struct GemmDev {
   int ntap, off_y, off_x;          // taps per axis (3 or 2), halo origin offset
   int o_scale, o_oy, o_ox, oH, oW; // output pixel mapping (phase of an upsample-folded conv)
   int gn_slot_off, gn_slots_img;
+  int wres;      // conv, weight-resident mode: number of A stages (0 = off); the whole per-CTA weight slab stays in smem
+  int w_tiles;   // weight tiles [B_ROWS x 64] of the slab = ntap^2 * c_blocks, tile t = (ky*ntap + kx)*c_blocks + cb
   // epilogue
   float alpha;
   const float* bias;
@@ -94,15 +96,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
-  float* staging = reinterpret_cast<float*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES) + Cfg::STG_BYTES);
+  // Weight-resident convs (p.wres): when a CTA's whole weight slab fits beside the A ring it is loaded ONCE per
+  // (persistent) CTA instead of once per tile: [slab: w_tiles x B_TAP_BYTES][A ring: wres stages]. The full-resolution
+  // N = 128, C = 128 convs are bound by L2 -> shared-memory traffic, more than half of which is the re-streamed weights.
+  const bool wres = CONV && p.wres > 0;
+  const int nstages = wres ? p.wres : STAGES;
+  const uint32_t slab_bytes = wres ? (uint32_t)p.w_tiles * Cfg::B_TAP_BYTES : 0u;
+  const uint32_t ring_bytes = wres ? slab_bytes + (uint32_t)p.wres * Cfg::A_BYTES : (uint32_t)(STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint8_t* smA = wres ? smem + slab_bytes : smem;
+  uint8_t* smB = wres ? smem : smem + STAGES * Cfg::A_BYTES;
+  float* staging = reinterpret_cast<float*>(smem + ring_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_bytes + Cfg::STG_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES] TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES] MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2] MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* w_full = bars + 2 * STAGES + 6;   // weight slab landed (resident mode)
+  static_assert((2 * STAGES + 7) * 8 <= Cfg::BAR_BYTES, "barrier block");
 
   // warp index through a shuffle: provably warp-uniform, so the producer / issuer branches are convergent and the
   // uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) are emitted directly; under a divergent `lane == 0` the
@@ -124,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], Cfg::EW * CG);  // epilogue warps of every CTA of the pair release the accumulator
     }
+    mbar_init(w_full, CG);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -150,6 +162,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (convergent warp, one lane issues)
     const bool leader = elect_one_sync();
+    if (wres && unit0 < p.num_tiles) {
+      // the CTA's weight slab (n_blocks == 1: rows [cta_rank * B_ROWS, +B_ROWS) of W, every K tile), once
+      if (leader) {
+        if (CG == 2) {
+          if (cta_rank == 0)
+            mbar_arrive_expect_tx(w_full, 2 * slab_bytes);
+          else
+            mbar_arrive_cluster(w_full, 0);
+        } else {
+          mbar_arrive_expect_tx(w_full, slab_bytes);
+        }
+        for (int t = 0; t < p.w_tiles; ++t) {
+          if (CG == 2)
+            tma_load_3d_2sm(smB + t * Cfg::B_TAP_BYTES, &tmW, w_full, t * BK, (int)cta_rank * Cfg::B_ROWS, 0);
+          else
+            tma_load_3d(smB + t * Cfg::B_TAP_BYTES, &tmW, w_full, t * BK, 0, 0);
+        }
+      }
+      __syncwarp();
+    }
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -169,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) {
           // conv: one halo box + ntap weight tiles per stage (ntap = 3, or 2 for an upsample-folded phase conv)
-          const uint32_t stage_tx = CONV ? (uint32_t)(Cfg::A_BYTES + p.ntap * Cfg::B_TAP_BYTES)
+          const uint32_t stage_tx = CONV ? (uint32_t)(Cfg::A_BYTES + (wres ? 0 : p.ntap * Cfg::B_TAP_BYTES))
                                          : (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES);
           if (CG == 2) {
             if (cta_rank == 0)
@@ -191,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           ty * CONV_BH + p.off_y, b);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-              if (ky >= p.ntap) break;
+              if (ky >= p.ntap || wres) break;
               const int kcol = ((ky * p.ntap + kx) * p.c_blocks + cb) * BK;
               if (CG == 2)
                 tma_load_3d_2sm(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
@@ -209,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }   // leader
           __syncwarp();
-          if (++stage == STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -224,6 +256,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (wres && unit0 < p.num_tiles) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
       for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
@@ -240,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (kb == p.k_blocks - 1) mbar_arrive(&tfull_bar[buf]);
             }
             __syncwarp();
-            if (++stage == STAGES) {
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -252,7 +288,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (ky >= TAPS) break;
             // conv: tap ky reads rows [16*ky, 16*ky + 128) of the halo box (+2048 B keeps the 1024 B swizzle phase)
             const uint64_t da = make_smem_desc_sw128(smem_u32(smA + stage * Cfg::A_BYTES + ky * (CONV_BW * BK * 2)));
-            const uint64_t db = make_smem_desc_sw128(smem_u32(smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES));
+            // resident slab: tile (ky, kx, cb) with kb = cb * ntap + kx; streamed: the stage's ky-th weight tile
+            const uint8_t* bt = wres ? smB + ((ky * p.ntap + (kb % p.ntap)) * p.c_blocks + kb / p.ntap) * Cfg::B_TAP_BYTES
+                                     : smB + stage * Cfg::B_BYTES + ky * Cfg::B_TAP_BYTES;
+            const uint64_t db = make_smem_desc_sw128(smem_u32(bt));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 32 B (16 bf16) inside the swizzle row: +2 in the 16 B-granular address field
@@ -271,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }   // leader
           __syncwarp();
-          if (++stage == STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -684,21 +723,49 @@ static int num_sms() {
 int device_num_sms() { return num_sms(); }
 int gemm_conv_tiles_per_image(int H, int W) { return ((W + CONV_BW - 1) / CONV_BW) * ((H + CONV_BH - 1) / CONV_BH); }
 
+static bool conv_wres_enabled() {
+  static const bool on = [] {
+    // Opt-in ("1"): measured neutral on B200 (interleaved A/B at 1024^2: 24.41 vs 24.30 ms; conv class 7.57 vs 7.57 ms), so
+    // the full-resolution N = 128 convs are NOT bound by re-streaming their weights; kept for experiments.
+    const char* e = getenv("IR_CONV_WRES");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 template <int BN, int EPI, bool CONV, int CG>
-static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t stream) {
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p_in, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG, CONV>;
+  constexpr int SMEM_MAX = 227 * 1024;
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
   static bool configured = false;
   if (!configured) {
-    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV ? SMEM_MAX : Cfg::SMEM_BYTES));
     configured = true;
   }
+  GemmDev p = p_in;
   const int slots = num_sms() / CG;
+  int smem_bytes = Cfg::SMEM_BYTES;
+  p.wres = 0;
+  p.w_tiles = 0;
+  if (CONV && p.n_blocks == 1 && conv_wres_enabled()) {
+    // weight-resident mode: the CTA's slab of ntap^2 * c_blocks weight tiles beside >= 3 A stages, and enough tiles per
+    // persistent CTA to amortise loading it
+    const long slab = (long)p.ntap * p.ntap * p.c_blocks * Cfg::B_TAP_BYTES;
+    long sa = (SMEM_MAX - 1024 - Cfg::STG_BYTES - Cfg::BAR_BYTES - slab) / Cfg::A_BYTES;
+    if (sa > Cfg::STAGES) sa = Cfg::STAGES;
+    const long tiles_per_cta = (p.num_tiles + slots - 1) / slots;
+    if (sa >= 3 && tiles_per_cta >= 3) {
+      p.wres = (int)sa;
+      p.w_tiles = p.ntap * p.ntap * p.c_blocks;
+      smem_bytes = 1024 + (int)slab + (int)sa * Cfg::A_BYTES + Cfg::STG_BYTES + Cfg::BAR_BYTES;
+    }
+  }
   const int grid = (p.num_tiles < slots ? p.num_tiles : slots) * CG;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
