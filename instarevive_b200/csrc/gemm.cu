@@ -35,9 +35,12 @@ struct GemmCfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int B_TAP_BYTES = B_ROWS * BK * 2;
   static constexpr int B_BYTES = (CONV ? 3 : 1) * B_TAP_BYTES;
-  // epilogue warps: 4 for the conv pipeline (no shared memory to spare), 8 for plain GEMMs (two per TMEM lane quarter,
-  // interleaved 32-column chunks): the residual / scatter epilogues are latency-bound, more warps = more loads in flight
-  static constexpr int EW = CONV ? 4 : 8;
+  // epilogue warps: 8 for plain GEMMs (two per TMEM lane quarter, interleaved 32-column chunks): the residual / scatter
+  // epilogues are latency-bound, more warps = more loads in flight. Convs: 8 where the second staging area does not cost
+  // a pipeline stage (per-CTA weight tiles of <= 64 rows: the 256x128 pair tiles and 128x64), 4 otherwise. The
+  // full-resolution N = 128 convs are epilogue-bound with 4 warps: 367 us (K = 1152) vs 526 us (K = 2304) at 1024^2 is a
+  // marginal MMA cost of 158 us per 309 GFLOP on top of ~209 us that does not scale with K (~6500 cycles per tile).
+  static constexpr int EW = CONV ? ((BN / CG <= 64) ? 8 : 4) : 8;
   static constexpr int NUM_THREADS = 128 + 32 * EW;
   static constexpr int STG_BYTES = EW * 32 * STG_LD * 4;
   static constexpr int BAR_BYTES = 256;
