@@ -293,3 +293,43 @@ def test_flavour_b_state_dict_is_diffusers_layout_and_generate_dispatch():
     out = generate.forward_model(m, lat, torch.tensor([400]), torch.randn(1, 1, 3, 4096), torch.ones(1, 1, 1, 3))
     assert out.shape == (1, 8, 8, 8) and rec.calls[-1]["y"].shape == (1, 1, 3, 4096)
     assert generate._is_flavour_b(m) and not generate._is_flavour_b(rec)
+
+
+# ------------------------------------------------------------------------------------------------ bench.py contract
+def test_bench_flop_model_matches_survey():
+    """SURVEY 8d [probe-verified with torch FlopCounter]: 4.362 TF per 512^2 image, 20.15 TF per 1024^2 image."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert abs(bench._flops_per_image(512) / 1e12 - 4.362) < 0.005
+    assert abs(bench._flops_per_image(1024) / 1e12 - 20.15) < 0.01
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: rank 0 prints ONE JSON line with the CUDA arm's metric / unit / config.workload, the
+    cpu_baseline block and a zero-copy e2e block; every other rank exits 0 without output (no GPU needed)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "restored_megapixels_per_second" and d["unit"] == "MP/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert "configs[1]" in d["config"]["workload"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
