@@ -28,7 +28,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "restored_megapixels_per_second"
 UNIT = "MP/s"
 IMG = 1024            # configs[1]: 1024x1024 single image per GPU
-CPU_SAMPLE = 256      # side of the bounded CPU sample (1/16 of the workload's pixels)
+CPU_SAMPLE = 512      # side of the bounded CPU sample: BASELINE configs[0], the reference's own CPU case (1/4 of the workload's pixels)
 DIT_FLOP_1024 = 9.683e12   # SURVEY 8d, torch FlopCounter on the reference (per 1024^2 image)
 VAE_FLOP_1024 = 10.47e12
 
@@ -98,7 +98,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_restore_sample(threads: int, side: int = CPU_SAMPLE, depth: int = 28, copy_blocks: int = 13, repeats: int = 1):
+def cpu_restore_sample(threads: int, side: int = CPU_SAMPLE, depth: int = 28, copy_blocks: int = 13, repeats: int = 2, warmup: int = 1):
     """The reference's algorithm (oracle port, fp32 torch on the CPU) on one side x side image. Returns (MP/s, seconds)."""
     import torch
     from instarevive_b200 import weights
@@ -109,12 +109,13 @@ def cpu_restore_sample(threads: int, side: int = CPU_SAMPLE, depth: int = 28, co
     h = side // 8
     x, _, y, mask, _ = weights.make_inputs(1, h, h, seed=0, lens=(77,))
     times = []
-    for _ in range(repeats):
+    for i in range(warmup + repeats):
         t0 = time.perf_counter()
         x0 = dit_oracle.generate_sample_1step(dit_sd, x, y, mask, depth=depth, copy_blocks=copy_blocks)
         img = vae_oracle.vae_decode(vae_sd, x0 / 0.18215) / 2 + 0.5
         _ = (img.clamp(0, 1) * 255).to(torch.uint8)
-        times.append(time.perf_counter() - t0)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
     return side * side / 1e6 / sec, sec
 
@@ -149,7 +150,7 @@ def run_reference(args):
     total = sum(times)
     mp = CPU_SAMPLE * CPU_SAMPLE / 1e6
     value = mp * args.steps / total
-    sample = (f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image (1/16 of the {IMG}x{IMG} workload's pixels) through the fp32 CPU port "
+    sample = (f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image (BASELINE configs[0]; 1/4 of the {IMG}x{IMG} workload's pixels) through the fp32 CPU port "
               "of the reference path (DiT+ControlNet 28+13 blocks, eps->x0, VAE decode)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -158,7 +159,7 @@ def run_reference(args):
         "config": {"workload": f"one-step restore {IMG}x{IMG} b1 per GPU (BASELINE.json configs[1])",
                    "network": "random-init PixArt-XL/2 (28 blocks) + ControlNet-Half(13) + SD-VAE decoder",
                    "parallelism": "host cores of rank 0 (torch intra-op threads); other ranks idle",
-                   "sample": f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image, 1/16 of the workload's pixels (the CPU path is "
+                   "sample": f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image, 1/4 of the workload's pixels (the CPU path is "
                              "linear in pixels except for the attention terms, which favours the CPU at the smaller size)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -359,7 +360,7 @@ def run_cuda(args):
             v, sec = cpu_restore_sample(cores)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"one {CPU_SAMPLE}x{CPU_SAMPLE} image through the fp32 CPU port of the reference path "
-                             f"(DiT+ControlNet 28+13, eps->x0, VAE decode), {sec:.1f} s, no warm-up"}
+                             f"(DiT+ControlNet 28+13, eps->x0, VAE decode; BASELINE configs[0]), median of 2 after 1 warm-up, {sec:.1f} s each"}
         flops_step = _flops_per_image(side) * nb if not tiled else None
         # the decoder's three "nearest x2 + 3x3 conv" layers run as 2x2 phase convs on the low-resolution input: 4/9 of
         # their 695.8 GFLOP per 512x512 image are executed. MFU is quoted on EXECUTED FLOPs.

@@ -60,11 +60,25 @@ def forward_model(model, latents, timestep, prompt_embeds, prompt_attention_mask
         if c is None:
             return model(latents, **kw).sample
         return model(latents, c=c, **kw)
-    data_info = {
-        "img_hw": torch.tensor([[float(h * 8), float(w * 8)]], device=latents.device).repeat(B, 1),
-        "aspect_ratio": torch.tensor([[float(h) / float(w)]], device=latents.device).repeat(B, 1),
-    }
-    return model(latents, ts, prompt_embeds, mask=prompt_attention_masks, data_info=data_info, c=c)
+    return model(latents, ts, prompt_embeds, mask=prompt_attention_masks, data_info=_micro_conditions(B, h, w, latents.device), c=c)
+
+
+_mc_cache: dict = {}
+
+
+def _micro_conditions(B: int, h: int, w: int, device):
+    """img_hw / aspect_ratio of generate.py:56-62 in pixels, cached per (batch, latent size, device): the reference
+    builds (and uploads) them on every call."""
+    key = (B, h, w, str(device))
+    hit = _mc_cache.get(key)
+    if hit is None:
+        if len(_mc_cache) > 64:
+            _mc_cache.clear()
+        hit = _mc_cache[key] = {
+            "img_hw": torch.tensor([[float(h * 8), float(w * 8)]], device=device).repeat(B, 1),
+            "aspect_ratio": torch.tensor([[float(h) / float(w)]], device=device).repeat(B, 1),
+        }
+    return hit
 
 
 def generate_sample_1step(model, scheduler, latents, maxt, prompt_embeds, prompt_attention_masks=None, c=None,
