@@ -333,3 +333,19 @@ def test_bench_reference_arm_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_decode_chunks_are_balanced_and_cover_the_shard():
+    """restore_latents decodes a rank's tiles in balanced chunks of at most decode_batch (25 -> 7+6+6+6): contiguous,
+    ordered, covering [s, e) exactly once (what keeps the all-gathered tile list in reference order)."""
+    from instarevive_b200.pipeline import shard_range
+    for n_mine in range(0, 40):
+        for cap in (1, 3, 8):
+            for s in (0, 5):
+                e = s + n_mine
+                n_chunks = (n_mine + cap - 1) // cap
+                bounds = [s + shard_range(n_mine, i, n_chunks)[0] for i in range(n_chunks)] + [e]
+                sizes = [b - a for a, b in zip(bounds[:-1], bounds[1:])]
+                assert sum(sizes) == n_mine and all(0 < z <= cap for z in sizes)
+                assert not sizes or max(sizes) - min(sizes) <= 1
+                assert bounds == sorted(bounds) and bounds[-1] == e and (not sizes or bounds[0] == s)
