@@ -1,12 +1,13 @@
-// Fused flash-attention forward for the DiT blocks: softmax(Q K^T / sqrt(d)) V without materialising the
-// score matrix. One kernel serves
-//   * self-attention (reference: AttentionKVCompress.forward, diffusion/model/nets/PixArt_blocks.py:123-158,
-//     xformers.ops.memory_efficient_attention with scale d^-1/2 and no mask), and
+// Fused flash-attention forward on the warp-level mma.sync path: softmax(Q K^T / sqrt(d)) V without materialising the
+// score matrix. In the product path it serves
 //   * cross-attention to the packed caption tokens (MultiHeadCrossAttention.forward, PixArt_blocks.py:43-58,
-//     BlockDiagonalMask.from_seqlens([T]*B, y_lens)): sample b attends to kv rows [kv_off[b], kv_off[b]+kv_len[b]).
+//     BlockDiagonalMask.from_seqlens([T]*B, y_lens)): sample b attends to kv rows [kv_off[b], kv_off[b]+kv_len[b]) --
+//     <= 300 keys, latency-bound: a CTA walks 2-4 consecutive query tiles with the caption K/V staged once and the next
+//     Q tile prefetched, the grid sized to one resident wave;
+// and, behind IR_ATTN_LEGACY=1 only, self-attention (AttentionKVCompress.forward, PixArt_blocks.py:123-158), whose
+// product kernel is the tcgen05 / TMEM one in attention_tc.cu.
 // head_dim is 72 (1152/16): rows are 144 B in global memory, staged to shared memory rows of 88 elements with the
 // K dimension zero-padded to 80 for the m16n8k16 tensor-core MMAs. fp32 online softmax (exp2 domain).
-// Round-1 implementation on the warp-level mma.sync path; the tcgen05/TMEM version is the planned upgrade.
 #include "attention.cuh"
 
 #include <cstdlib>

@@ -2,8 +2,11 @@
 // ldm/modules/diffusionmodules/model.py:622-655) on NHWC bf16 activations:
 //   * 3x3 convolutions and 1x1 convolutions run on the tcgen05 implicit-GEMM / GEMM kernel (gemm.cu),
 //     bias and the residual add fused into the epilogue;
-//   * GroupNorm(32, eps 1e-6) statistics (deterministic two-stage reduction) + normalise + SiLU -> bf16,
-//     nearest x2 upsample, conv_in (K = 36) and conv_out (N = 3) are fused HBM-bound kernels here;
+//   * GroupNorm(32, eps 1e-6): statistics from the producing conv / GEMM epilogue (standalone two-stage reduction for
+//     conv_in's output only), normalise + SiLU -> bf16 as one HBM-bound pass; conv_in (K = 36) is a fused kernel here;
+//   * Upsample.forward (nearest x2 + 3x3 conv) runs as four 2x2 phase convs on the low-resolution input with pre-summed
+//     weights (4/9 of the FLOPs, no upsampled tensor); conv_out (N = 3) as a tap-response GEMM (N = 27) + 9-neighbour
+//     gather-sum;
 //   * the mid-block single-head attention (d = 512) materialises the score matrix through the GEMM kernel
 //     (B200 has the HBM for it) with a row softmax in fp32.
 #include "vae.cuh"
