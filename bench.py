@@ -7,7 +7,12 @@
 A step = one one-step restore of one synthetic degraded 1024x1024 image per GPU (configs[1] of BASELINE.json; weak
 scaling: every rank restores its own image, images are independent -- SURVEY 8e): DiT+ControlNet forward (28+13 blocks,
 random-init XL/2 weights) -> eps->x0 -> VAE decode -> [0,1] image. `value` times that with inputs resident in HBM;
-`e2e` times the public process() call with the HOST uint8 image (H2D, synthetic encode, restore, uint8, D2H inside).
+`e2e` times the public process() call with the HOST uint8 image (H2D, VAE encode on this repo's own encoder kernels,
+restore, uint8, D2H inside); `e2e_full_cli` adds the stage-1 SwinIR the CLI runs by default.
+
+The same line carries a `tiled_2048` block: BASELINE configs[3], ONE 2048x2048 image whose 25 latent tiles are sharded
+over the N ranks (strong scaling; all-gather of tile latents, ordered blend, all-gather of decoded tiles), timed with
+the same event discipline, with per-phase times and the output CRC (identical for every N).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -28,7 +33,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "restored_megapixels_per_second"
 UNIT = "MP/s"
 IMG = 1024            # configs[1]: 1024x1024 single image per GPU
-CPU_SAMPLE = 512      # side of the bounded CPU sample: BASELINE configs[0], the reference's own CPU case (1/4 of the workload's pixels)
+CPU_SAMPLE = 1024     # side of the CPU sample: the workload itself (one 1024x1024 image, configs[1]) -- same config as the CUDA arm
 DIT_FLOP_1024 = 9.683e12   # SURVEY 8d, torch FlopCounter on the reference (per 1024^2 image)
 VAE_FLOP_1024 = 10.47e12
 
@@ -50,6 +55,67 @@ def _peaks():
         d = json.loads(p.read_text())
         return d.get("bf16_tflops_sustained", 1393.6), d.get("hbm_gbs", 6543.1), "measured (MEASURED_PEAKS.json, sustained)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic_from_profiles():
+    """DRAM traffic of the gemm_tc_kernel family from the committed `ncu --set full` capture of one 1024x1024 step
+    (profiles/r02_gemm_traffic_by_shape.json, written by tools/ncu_traffic_by_shape.py from the ncu CSV joined with the
+    library's own per-launch shape log). Returns (mean bytes per launch over the family's launches of the step -- the same
+    averaging as `achieved` --, source string, per-shape rows with the shape's algorithmic bytes beside its traffic)."""
+    p = ROOT / "profiles" / "r02_gemm_traffic_by_shape.json"
+    if not p.exists():
+        return None, None, None
+    try:
+        d = json.loads(p.read_text())
+        return d.get("mean_dram_bytes_per_launch"), d.get("source"), d.get("shapes")
+    except Exception:
+        return None, None, None
+
+
+CLASS_NAMES = {0: "gemm", 1: "conv", 2: "attention", 3: "cross_attention"}
+
+
+def _shape_table(L, steps: int, dump_path=None):
+    """Per-shape view of the profile pass that is running (ir_profile_records): for every distinct (class, M, N, K) the
+    launches per step, the mean launch duration (CUDA events on the launching stream), TFLOP/s and the shape's
+    ALGORITHMIC bytes (operands read once + outputs written once). With dump_path the per-launch shape list of one step is
+    written in launch order, for tools/ncu_traffic_by_shape.py to join with an ncu capture of the same command."""
+    import ctypes as C
+    n = int(L.ir_profile_records(None, None, None, None, None, 0))
+    if n <= 0:
+        return None
+    kl, M, N, K, ms = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)(), (C.c_float * n)()
+    L.ir_profile_records(kl, M, N, K, ms, n)
+    agg = {}
+    for i in range(n):
+        key = (kl[i], M[i], N[i], K[i])
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += ms[i]
+    rows = []
+    for (k, m, nn, kk), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        if k in (0, 1):
+            flops = 2.0 * m * nn * kk
+            # GEMM: A (M x K) + W (N x K) bf16 read, out (M x N) written (bf16; the fp32-residual epilogues move 3x that);
+            # conv: the activation is M x Cin = M x K / taps^2 (not the im2col matrix)
+            a_bytes = 2.0 * m * (kk if k == 0 else (kk // 9 if kk % 9 == 0 else kk // 4))
+            alg = a_bytes + 2.0 * nn * kk + 2.0 * m * nn
+        elif k == 2:
+            flops = 4.0 * m * nn * nn * kk
+            alg = 4 * 2.0 * m * nn * kk   # q, k, v read + o written, bf16
+        else:
+            flops, alg = 0.0, None
+        us = 1e3 * t / c
+        rows.append({"class": CLASS_NAMES.get(k, str(k)), "M": m, "N": nn, "K": kk, "launches_per_step": c / steps,
+                     "avg_us": us, "ms_per_step": t / steps, "tflops": flops / (us * 1e-6) / 1e12 if flops else None,
+                     "algorithmic_bytes": alg})
+    if dump_path:
+        per_step = n // steps
+        seq = [{"i": i, "class": CLASS_NAMES.get(kl[i], str(kl[i])), "M": M[i], "N": N[i], "K": K[i], "us": 1e3 * ms[i]}
+               for i in range(n - per_step, n)]
+        Path(dump_path).parent.mkdir(parents=True, exist_ok=True)
+        Path(dump_path).write_text(json.dumps(seq))
+    return rows[:24]
 
 
 class ClockSampler:
@@ -98,30 +164,43 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_restore_sample(threads: int, side: int = CPU_SAMPLE, depth: int = 28, copy_blocks: int = 13, repeats: int = 2, warmup: int = 1):
-    """The reference's algorithm (oracle port, fp32 torch on the CPU) on one side x side image. Returns (MP/s, seconds)."""
+def cpu_restore_sample(threads: int, side: int = CPU_SAMPLE, depth: int = 28, copy_blocks: int = 13, repeats: int = 1):
+    """The reference's algorithm (oracle port, fp32 torch on the CPU; pinned to the unmodified reference's outputs at
+    this very size by tests/test_oracle_slow.py) on one side x side image. Returns (MP/s, seconds)."""
     import torch
     from instarevive_b200 import weights
     from oracle import dit_oracle, vae_oracle
     torch.set_num_threads(threads)
     dit_sd = weights.make_dit_state_dict(depth=depth, copy_blocks=copy_blocks, seed=1)
     vae_sd = weights.make_vae_decoder_state_dict(seed=2)
-    h = side // 8
-    x, _, y, mask, _ = weights.make_inputs(1, h, h, seed=0, lens=(77,))
-    times = []
-    for i in range(warmup + repeats):
+
+    def one(sz):
+        h = sz // 8
+        x, _, y, mask, _ = weights.make_inputs(1, h, h, seed=0, lens=(77,))
         t0 = time.perf_counter()
         x0 = dit_oracle.generate_sample_1step(dit_sd, x, y, mask, depth=depth, copy_blocks=copy_blocks)
         img = vae_oracle.vae_decode(vae_sd, x0 / 0.18215) / 2 + 0.5
         _ = (img.clamp(0, 1) * 255).to(torch.uint8)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    sec = statistics.median(times)
+        return time.perf_counter() - t0
+
+    one(128)   # spins up the intra-op thread pool and the allocator (a fraction of a second)
+    sec = statistics.median([one(side) for _ in range(repeats)])
     return side * side / 1e6 / sec, sec
 
 
+def make_config(side: int, nb: int, world: int, depth: int, cb: int, tiled: bool):
+    """The `config` object of the JSON line; the reference arm prints the very same one (same workload, same network)."""
+    return {"workload": (f"tiled {side}x{side} restore, tile 512/448, tiles sharded over {world} GPU(s)" if tiled else
+                         f"one-step restore {side}x{side} b{nb} per GPU" + (" (BASELINE.json configs[1])" if (side, nb) == (IMG, 1) else "")),
+            "network": f"random-init PixArt-XL/2 ({depth} blocks) + ControlNet-Half({cb}) + SD-VAE decoder",
+            "parallelism": f"dp{world} (images/tiles sharded, weights replicated)",
+            "l2": "no flush: the per-step working set (1.9 GB bf16 weights + activations) exceeds the 126 MB L2",
+            "caption": "120-token synthetic T5 embedding, 77 valid; caption K/V cached across steps (constant per run)"}
+
+
 def run_reference(args):
-    """`--impl reference`: rank 0 alone times the CPU port; other ranks exit 0 without work."""
+    """`--impl reference`: rank 0 alone times the CPU port of the reference path on the host cores, on the CUDA arm's own
+    workload (one 1024x1024 image per step); other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -130,13 +209,14 @@ def run_reference(args):
     from oracle import dit_oracle, vae_oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    dit_sd = weights.make_dit_state_dict(depth=28, copy_blocks=13, seed=1)
+    dit_sd = weights.make_dit_state_dict(depth=args.depth, copy_blocks=args.copy_blocks, seed=1)
     vae_sd = weights.make_vae_decoder_state_dict(seed=2)
-    h = CPU_SAMPLE // 8
+    side = args.size
+    h = side // 8
     x, _, y, mask, _ = weights.make_inputs(1, h, h, seed=0, lens=(77,))
 
     def step():
-        x0 = dit_oracle.generate_sample_1step(dit_sd, x, y, mask)
+        x0 = dit_oracle.generate_sample_1step(dit_sd, x, y, mask, depth=args.depth, copy_blocks=args.copy_blocks)
         img = vae_oracle.vae_decode(vae_sd, x0 / 0.18215) / 2 + 0.5
         return (img.clamp(0, 1) * 255).to(torch.uint8)
 
@@ -148,22 +228,21 @@ def run_reference(args):
         step()
         times.append(time.perf_counter() - t0)
     total = sum(times)
-    mp = CPU_SAMPLE * CPU_SAMPLE / 1e6
+    mp = side * side / 1e6
     value = mp * args.steps / total
-    sample = (f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image (BASELINE configs[0]; 1/4 of the {IMG}x{IMG} workload's pixels) through the fp32 CPU port "
-              "of the reference path (DiT+ControlNet 28+13 blocks, eps->x0, VAE decode)")
+    sample = (f"each step = one {side}x{side} image (the CUDA arm's own per-GPU workload) through the fp32 CPU port of the "
+              f"reference path (DiT+ControlNet {args.depth}+{args.copy_blocks} blocks, eps->x0, VAE decode) on {cores} host threads; "
+              "the port is pinned to the unmodified reference's outputs at this size (tests/test_oracle_slow.py: "
+              "dit_full_b1_128x128, vae_b1_128x128 goldens)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"one-step restore {IMG}x{IMG} b1 per GPU (BASELINE.json configs[1])",
-                   "network": "random-init PixArt-XL/2 (28 blocks) + ControlNet-Half(13) + SD-VAE decoder",
-                   "parallelism": "host cores of rank 0 (torch intra-op threads); other ranks idle",
-                   "sample": f"each step = one {CPU_SAMPLE}x{CPU_SAMPLE} image, 1/4 of the workload's pixels (the CPU path is "
-                             "linear in pixels except for the attention terms, which favours the CPU at the smaller size)"},
+        "config": make_config(side, 1, max(1, args.gpus), args.depth, args.copy_blocks, False),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p50_ms_per_image": 1e3 * statistics.median(times), "gpu_launches": 0,
+        "note": "rank 0's host cores only (torch intra-op threads); the other ranks idle",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -171,6 +250,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_cuda(args):
+    import zlib
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -191,72 +272,78 @@ def run_cuda(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    _lib.lib()
+    L = _lib.lib()
 
     depth, cb = args.depth, args.copy_blocks
     net = ir.ControlPixArtMSHalf(ir.PixArtMS(depth=depth, input_size=64, micro_condition=True, init_weights=False), cb).eval()
     net.load_state_dict(weights.make_dit_state_dict(depth=depth, copy_blocks=cb, seed=1), strict=True)
     net = net.to(dev)
     net.pack()
-    enc = weights.SyntheticVAE(None)
-    vae = ir.AutoencoderKLDecoder(weights.make_vae_decoder_state_dict(seed=2), device=dev, encoder=enc.encode)
+    # encoder + decoder on this repo's own kernels: nothing from cuDNN / ATen convolutions runs in any timed region
+    vae = ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=dev)
     sched = ir.DDPMSchedulerLite()
-    side = args.size
     _, _, y, mask, _ = weights.make_inputs(1, 8, 8, seed=9, lens=(77,))
     y, mask = y.to(dev), mask.to(dev)
-    nb = 1 if args.workload == "tiled" else max(1, args.batch)   # images per GPU and step (BASELINE configs[2], [4])
-    imgs_u8 = [weights.synthetic_degraded_image(side, side, seed=0 if args.workload == 'tiled' else rank * nb + i)
-               for i in range(nb)]
-    host_img = torch.from_numpy(np.stack(imgs_u8)).pin_memory()
-    host_list = [host_img[i].numpy() for i in range(nb)]
-    control = host_img.to(dev).float().div(255.0).permute(0, 3, 1, 2).contiguous()
-    init_noise = (enc.encode(control * 2 - 1).latent_dist.mode() * 0.18215).contiguous()
-    tiled = args.workload == "tiled"
-
-    def step_resident():
-        return pipeline.restore_latents(net, vae, control, init_noise, y, mask, tiled=tiled, scheduler=sched)
-
-    def step_e2e():
-        preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
-                              tiled=tiled, tile_size=512, tile_stride=448, vae=vae, y=y, y_mask=mask, scheduler=sched)
-        return preds
+    steps, warm = args.steps, max(3, args.warmup)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
+    def timed(fn, nsteps, nwarm):
+        for _ in range(nwarm):
             fn()
         barrier()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps + 1)]
         evs[0].record()
-        for i in range(steps):
+        for i in range(nsteps):
             fn()
             evs[i + 1].record()
         barrier()
         total = evs[0].elapsed_time(evs[-1])
-        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(nsteps)]
         if world > 1:
             t = torch.tensor([total], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total = float(t.item())
         return total, per
 
+    def load_images(side, seeds):
+        imgs_u8 = [weights.synthetic_degraded_image(side, side, seed=sd) for sd in seeds]
+        host_img = torch.from_numpy(np.stack(imgs_u8)).pin_memory()
+        host_list = [host_img[i].numpy() for i in range(len(seeds))]
+        control = host_img.to(dev).float().div(255.0).permute(0, 3, 1, 2).contiguous()
+        init_noise = (vae.encode(control * 2 - 1).latent_dist.mode() * 0.18215).contiguous()
+        return host_img, host_list, control, init_noise
+
+    def crc_of(img):
+        torch.cuda.synchronize()
+        return zlib.crc32(pipeline.to_uint8_nhwc(img[:1]).cpu().numpy().tobytes())
+
+    # ================================================================== headline workload
+    tiled = args.workload == "tiled"
+    side = args.size
+    nb = 1 if tiled else max(1, args.batch)   # images per GPU and step (BASELINE configs[2], [4])
+    host_img, host_list, control, init_noise = load_images(side, [0] if tiled else [rank * nb + i for i in range(nb)])
+
+    def step_resident():
+        return pipeline.restore_latents(net, vae, control, init_noise, y, mask, tiled=tiled, scheduler=sched, use_control=True)
+
+    def step_e2e(pre=None):
+        preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=pre is None,
+                              preprocess_model=pre, tiled=tiled, tile_size=512, tile_stride=448, vae=vae, y=y, y_mask=mask,
+                              scheduler=sched, use_control=True)
+        return preds
+
     mp_per_step = side * side / 1e6 * (1 if tiled else world * nb)  # tiled: one image sharded over all ranks
     clocks = ClockSampler(local)
     launches0 = _lib.launch_count()
-    total_ms, per = timed(step_resident, args.steps, max(3, args.warmup))
+    total_ms, per = timed(step_resident, steps, warm)
     launches = _lib.launch_count() - launches0
     clk = clocks.stop()
-    value = mp_per_step * args.steps / (total_ms / 1e3)
-
-    # checksum of one restored image (tiled workload: must be identical for every world size -- bit-exact sharding)
-    import zlib
-    chk_img = step_resident()
-    torch.cuda.synchronize()
-    checksum = zlib.crc32(pipeline.to_uint8_nhwc(chk_img[:1]).cpu().numpy().tobytes())
+    value = mp_per_step * steps / (total_ms / 1e3)
+    checksum = crc_of(step_resident())
 
     # one extra resident step inside a cudaProfilerStart/Stop range (outside every timed region) so that the same
     # command can be profiled with `ncu --profile-from-start off` (profiles/README.md)
@@ -266,128 +353,148 @@ def run_cuda(args):
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
-    # end to end through the public process() call with a host image
-    e2e_ms, _ = timed(step_e2e, args.steps, 1)
-    e2e_value = mp_per_step * args.steps / (e2e_ms / 1e3)
+    # end to end through the public process() call: host uint8 image -> H2D -> VAE encode (this repo's encoder kernels)
+    # -> restore -> uint8 -> D2H. `e2e_full_cli` adds the stage-1 SwinIR, which the CLI runs unless told otherwise.
+    e2e_ms, _ = timed(step_e2e, steps, 2)
+    e2e_value = mp_per_step * steps / (e2e_ms / 1e3)
     h2d = int(host_img.numel())      # process() uploads the uint8 HWC image and normalises it on the device
     d2h = int(host_img.numel()) * 2  # restored image + stage-1 image, uint8
-
-    # SURVEY 8f row 1 (the step right before the path), measured to the same bar: the VAE encoder on the device, alone
-    # and inside process() (host uint8 image -> encode -> restore -> uint8 on the host)
-    enc_info = None
+    side_info = None
+    e2e_cli = None
     if not args.no_encoder:
-        vae_full = ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=dev)
         x_img = (control * 2 - 1).contiguous()
-
-        def step_encode():
-            return vae_full.encode(x_img).latent_dist.mode()
-
-        def step_e2e_native():
-            preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=True,
-                                  tiled=tiled, tile_size=512, tile_stride=448, vae=vae_full, y=y, y_mask=mask, scheduler=sched)
-            return preds
-
-        enc_ms, _ = timed(step_encode, args.steps, 2)
-        e2e_nat_ms, _ = timed(step_e2e_native, args.steps, 1)
+        enc_ms, _ = timed(lambda: vae.encode(x_img).latent_dist.mode(), steps, 2)
         enc_flops = 4.5e12 * (side / 1024.0) ** 2 * nb   # 1.12 TFLOP per 512x512 image
-        enc_info = {"ms_per_image": enc_ms / args.steps / nb, "tflops": enc_flops / (enc_ms / args.steps / 1e3) / 1e12,
-                    "e2e_with_native_encoder": {"value": mp_per_step * args.steps / (e2e_nat_ms / 1e3), "unit": UNIT,
-                                                "ms_per_step": e2e_nat_ms / args.steps},
-                    "note": "AutoencoderKL.encode of the whole image on the device (reference: inference.py:104-109); "
-                            "outside the north-star metric, reported beside it"}
-        del vae_full
-        torch.cuda.empty_cache()
-        # the stage-1 SwinIR on the same image
+        side_info = {"vae_encode_ms_per_image": enc_ms / steps / nb,
+                     "vae_encode_tflops": enc_flops / (enc_ms / steps / 1e3) / 1e12,
+                     "note": "AutoencoderKL.encode of the whole image (inference.py:104-109) and SwinIR.forward "
+                             "(configs/swinir.yaml) on the device; outside the north-star metric, inside e2e / e2e_full_cli"}
         swin = ir.SwinIR(weights.make_swinir_state_dict(seed=7), device=dev)
-        swin_ms, _ = timed(lambda: swin(control), args.steps, 2)
-        enc_info["swinir_stage1"] = {"ms_per_image": swin_ms / args.steps / nb,
-                                     "note": "SwinIR.forward (configs/swinir.yaml) of the whole image on the device"}
+        swin_ms, _ = timed(lambda: swin(control), steps, 2)
+        side_info["swinir_stage1_ms_per_image"] = swin_ms / steps / nb
+        cli_ms, _ = timed(lambda: step_e2e(swin), steps, 2)
+        e2e_cli = {"value": mp_per_step * steps / (cli_ms / 1e3), "unit": UNIT, "ms_per_step": cli_ms / steps,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "api": "instarevive_b200.process(model, [uint8 HWC image], preprocess_model=SwinIR, ...): stage-1 SwinIR -> "
+                          "VAE encode -> restore -> uint8, the scripts/inference.py default path"}
         del swin
         torch.cuda.empty_cache()
 
-    # per-kernel roofline pass: the same steps re-run with CUDA events around every launch of the GEMM family
-    L = _lib.lib()
-    prof = None
-    if True:
-        L.ir_profile_begin()
-        for _ in range(args.steps):
-            step_resident()
-        torch.cuda.synchronize()
-        import ctypes as C
-        ms = (C.c_double * 8)()
-        fl = (C.c_double * 8)()
-        cnt = (C.c_longlong * 8)()
-        L.ir_profile_end(ms, fl, cnt)
-        prof = {"gemm": (ms[0], fl[0], cnt[0]), "conv": (ms[1], fl[1], cnt[1]), "attention": (ms[2], fl[2], cnt[2]),
-                "cross_attention": (ms[3], fl[3], cnt[3])}
+    # per-kernel roofline pass: the same steps re-run with CUDA events around every launch of the tensor-core kernels
+    import ctypes as C
+    L.ir_profile_begin()
+    for _ in range(steps):
+        step_resident()
+    torch.cuda.synchronize()
+    by_shape_live = _shape_table(L, steps, args.dump_shapes if rank == 0 else None)
+    ms = (C.c_double * 8)()
+    fl = (C.c_double * 8)()
+    cnt = (C.c_longlong * 8)()
+    L.ir_profile_end(ms, fl, cnt)
+    prof = {"gemm": (ms[0], fl[0], cnt[0]), "conv": (ms[1], fl[1], cnt[1]), "attention": (ms[2], fl[2], cnt[2]),
+            "cross_attention": (ms[3], fl[3], cnt[3])}
     peak_tf, peak_hbm, peak_src = _peaks()
-    # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture (profiles/)
-    traffic = None
-    traffic_src = None
-    try:
-        import csv
-        with open(ROOT / "profiles" / "r01_ncu_full_step_summary.csv") as f:
-            rows = list(csv.reader(f))
-        hdr, units = rows[0], rows[1]
-        ir_, iw_, in_ = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        vals = [float(r[ir_]) * scale.get(units[ir_], 1.0) + float(r[iw_]) * scale.get(units[iw_], 1.0)
-                for r in rows[2:] if "gemm_tc_kernel" in r[in_]]
-        if vals:
-            traffic = sum(vals) / len(vals)   # bytes per launch, averaged over the captured launches
-            traffic_src = (f"profiles/r01_ncu_full_step_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean of "
-                           f"{len(vals)} gemm_tc_kernel launches of one 1024x1024 step (ncu --set full, L2 flushed per launch)")
-    except Exception:
-        traffic = None
-    roofline = None
-    kernels = None
-    if prof:
-        g_ms = prof["gemm"][0] + prof["conv"][0]
-        g_fl = prof["gemm"][1] + prof["conv"][1]
-        g_n = prof["gemm"][2] + prof["conv"][2]
-        ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-        roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "launches": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
-                    "share_of_step": g_ms / args.steps / (total_ms / args.steps)}
-        kernels = {k: {"ms_per_step": v[0] / args.steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12) if v[0] > 0 else None,
-                       "launches_per_step": v[2] / args.steps} for k, v in prof.items()}
+    g_ms = prof["gemm"][0] + prof["conv"][0]
+    g_fl = prof["gemm"][1] + prof["conv"][1]
+    g_n = prof["gemm"][2] + prof["conv"][2]
+    ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    traffic, traffic_src, by_shape = _traffic_from_profiles()
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)", "bound": "tensor", "achieved": ach,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_by_shape": by_shape, "peak_source": peak_src,
+                "launches": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
+                "share_of_step": g_ms / steps / (total_ms / steps)}
+    roofline["by_shape"] = by_shape_live
+    kernels = {k: {"ms_per_step": v[0] / steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12) if v[0] > 0 else None,
+                   "launches_per_step": v[2] / steps} for k, v in prof.items()}
+
+    # ================================================================== tiled 2048^2 (BASELINE configs[3]), strong scaling
+    tiled_block = None
+    if not tiled and not args.no_tiled:
+        tiled_block = run_tiled_block(args, ir, pipeline, weights, net, vae, sched, y, mask, dev, world, rank, timed, crc_of,
+                                      load_images)
 
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec = cpu_restore_sample(cores)
+            v, sec = cpu_restore_sample(cores, side=side if not tiled else CPU_SAMPLE)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"one {CPU_SAMPLE}x{CPU_SAMPLE} image through the fp32 CPU port of the reference path "
-                             f"(DiT+ControlNet 28+13, eps->x0, VAE decode; BASELINE configs[0]), median of 2 after 1 warm-up, {sec:.1f} s each"}
+                   "sample": f"one {side if not tiled else CPU_SAMPLE}x{side if not tiled else CPU_SAMPLE} image (the headline workload itself) through the "
+                             f"fp32 CPU port of the reference path (DiT+ControlNet 28+13, eps->x0, VAE decode), one run of {sec:.1f} s "
+                             "after a 128x128 thread-pool warm-up; the port is pinned to the unmodified reference at this size"}
         flops_step = _flops_per_image(side) * nb if not tiled else None
         # the decoder's three "nearest x2 + 3x3 conv" layers run as 2x2 phase convs on the low-resolution input: 4/9 of
         # their 695.8 GFLOP per 512x512 image are executed. MFU is quoted on EXECUTED FLOPs.
         exec_step = (flops_step - (5.0 / 9.0) * 695.8e9 * (side / 512.0) ** 2 * nb) if flops_step else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong" if tiled else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": (f"tiled {side}x{side} restore, tile 512/448, tiles sharded over {world} GPU(s)" if tiled else
-                                    f"one-step restore {side}x{side} b{nb} per GPU" + (" (BASELINE.json configs[1])" if (side, nb) == (IMG, 1) else "")),
-                       "network": f"random-init PixArt-XL/2 ({depth} blocks) + ControlNet-Half({cb}) + SD-VAE decoder",
-                       "parallelism": f"dp{world} (images/tiles sharded, weights replicated)",
-                       "l2": "no flush: the per-step working set (1.9 GB bf16 weights + activations) exceeds the 126 MB L2",
-                       "caption": "120-token synthetic T5 embedding, 77 valid; caption K/V cached across steps (constant per run)"},
+            "config": make_config(side, nb, world, depth, cb, tiled),
             "p50_ms_per_image": statistics.median(per) / nb,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "api": "instarevive_b200.process(model, [uint8 HWC image], ...)"},
+                    "ms_per_step": e2e_ms / steps,
+                    "api": "instarevive_b200.process(model, [uint8 HWC image], ...): H2D -> VAE encode (own kernels) -> restore -> uint8 -> D2H"},
+            "e2e_full_cli": e2e_cli,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
             "model_tflops_per_step": flops_step / 1e12 if flops_step else None,
             "executed_tflops_per_step": exec_step / 1e12 if exec_step else None, "output_crc32": checksum,
-            "vae_encode": enc_info,
-            "mfu_vs_measured_peak": (exec_step / (total_ms / args.steps / 1e3) / 1e12 / peak_tf) if exec_step else None,
+            "side_measurements": side_info, "tiled_2048": tiled_block,
+            "mfu_vs_measured_peak": (exec_step / (total_ms / steps / 1e3) / 1e12 / peak_tf) if exec_step else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_tiled_block(args, ir, pipeline, weights, net, vae, sched, y, mask, dev, world, rank, timed, crc_of, load_images):
+    """BASELINE configs[3]: ONE 2048x2048 image, 25 latent tiles of 512/448 sharded over the ranks (strong scaling), the two
+    all-gathers inside the timed region. Every rank holds the same image; rank 0 reports."""
+    import torch
+    import torch.distributed as dist
+    side = 2048
+    host_img, host_list, control, init_noise = load_images(side, [0])
+    nsteps = max(3, min(args.steps, 10))
+
+    def step():
+        return pipeline.restore_latents(net, vae, control, init_noise, y, mask, tiled=True, scheduler=sched, use_control=True)
+
+    def step_e2e():
+        preds, _ = ir.process(net, host_list, strength=1, color_fix_type="wavelet", disable_preprocess_model=True, tiled=True,
+                              tile_size=512, tile_stride=448, vae=vae, y=y, y_mask=mask, scheduler=sched, use_control=True)
+        return preds
+
+    clocks = ClockSampler(dev.index)
+    total_ms, per = timed(step, nsteps, 3)
+    clk = clocks.stop()
+    crc = crc_of(step())
+    # per-phase times (CUDA events at the phase boundaries; a separate pass so the headline number carries no extra events)
+    timer = pipeline.PhaseTimer()
+    for _ in range(3):
+        pipeline.restore_latents(net, vae, control, init_noise, y, mask, tiled=True, scheduler=sched, use_control=True, timer=timer)
+    torch.cuda.synchronize()
+    phases = {k: v / 3 for k, v in timer.summary().items()}
+    if world > 1:   # slowest rank per phase (what the step waits for)
+        keys = sorted(phases)
+        t = torch.tensor([phases[k] for k in keys], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(keys, t.tolist())}
+    e2e_ms, _ = timed(step_e2e, nsteps, 1)
+    mp = side * side / 1e6
+    nt = len(pipeline._sliding_windows(side // 8, side // 8, 64, 56))
+    limiting = max(phases, key=phases.get) if phases else None
+    return {"workload": f"tiled {side}x{side} restore, tile 512/448, {nt} tiles sharded over {world} GPU(s) (BASELINE.json configs[3])",
+            "scaling": "strong", "value": mp * nsteps / (total_ms / 1e3), "unit": UNIT, "ms_per_step": total_ms / nsteps,
+            "p50_ms_per_image": statistics.median(per), "steps": nsteps, "output_crc32": crc,
+            "e2e": {"value": mp * nsteps / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms / nsteps,
+                    "h2d_bytes_per_step": int(host_img.numel()), "d2h_bytes_per_step": int(host_img.numel()) * 2,
+                    "note": "process(tiled=True) with the host image; the whole-image VAE encode is replicated on every rank "
+                            "(global attention / GroupNorm: it does not shard), so e2e scales worse than the restore itself"},
+            "phases_ms": phases, "limiting_phase": limiting,
+            "tiles_per_rank_max": -(-nt // world), "speedup_bound_vs_1gpu": nt / float(-(-nt // world)),
+            "clocks": clk}
 
 
 def main():
@@ -402,7 +509,9 @@ def main():
     ap.add_argument("--depth", type=int, default=28)
     ap.add_argument("--copy-blocks", type=int, default=13)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-encoder", action="store_true", help="skip the VAE-encoder side measurement (SURVEY 8f row 1)")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the VAE-encoder / SwinIR side measurements and e2e_full_cli")
+    ap.add_argument("--dump-shapes", default=None, help="write the per-launch shape list of one profiled step (JSON) here")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the tiled_2048 block (BASELINE configs[3])")
     args = ap.parse_args()
     if args.size is None:
         args.size = 2048 if args.workload == "tiled" else IMG

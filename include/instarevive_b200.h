@@ -54,6 +54,10 @@ long long ir_launch_count(void);
  * the summed algorithmic FLOPs and the launch counts. Not thread-safe; not for use inside CUDA-graph capture. */
 void ir_profile_begin(void);
 int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launches_by_class);
+/* Per-launch records of the running profile pass, in launch order: class, problem shape (GEMM: M x N x K with the batch
+ * folded into M; conv: pixels x Cout x taps*Cin; self-attention: B*heads, T, head_dim) and duration in ms. Call after the
+ * work was enqueued and before ir_profile_end; synchronises the device. Returns the record count (only `cap` written). */
+long long ir_profile_records(int* klass, int* M, int* N, int* K, float* ms, long long cap);
 
 /* ------------------------------------------------------------------ DiT + ControlNet-Half ---- */
 typedef struct ir_dit ir_dit; /* opaque: packed weights of one (device, model) */
@@ -80,6 +84,10 @@ int ir_dit_param_info(const ir_dit* h, int i, char* name, int name_cap, long lon
 /* Copy one fp32 parameter (device pointer, reference layout) into the packed device representation. */
 int ir_dit_load_param(ir_dit* h, const char* name, const float* src_dev, long long numel, void* stream);
 size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l);
+/* Pre-size the caches the handle owns -- the 2-D sincos position table (PixArt.py:258-307; up to max_tokens tokens) and the
+ * caption K/V of all blocks (PixArt_blocks.py:47-50; up to max_sum_l packed caption tokens) -- so that no forward calls
+ * cudaMalloc. Optional: forwards grow the buffers on demand (grow-only, never freed before ir_dit_destroy). */
+int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l);
 /*
  * x, c: (B,4,H,W) fp32 latents (c may be NULL: plain 28-block path); timestep: (B) fp32;
  * y: (rows,4096) fp32 caption embeddings; y_index: device int32 (sum_l) valid rows of y, sample-major;

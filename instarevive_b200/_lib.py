@@ -33,12 +33,14 @@ PROTOTYPES = {
     "ir_launch_count": (_ll, []),
     "ir_profile_begin": (None, []),
     "ir_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
+    "ir_profile_records": (_ll, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _ll]),
     "ir_dit_create": (_i, [C.POINTER(DitConfig), C.POINTER(_vp)]),
     "ir_dit_destroy": (None, [_vp]),
     "ir_dit_num_params": (_i, [_vp]),
     "ir_dit_param_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_ll), C.POINTER(_i), C.POINTER(_i)]),
     "ir_dit_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
     "ir_dit_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
+    "ir_dit_reserve": (_i, [_vp, _i, _i]),
     "ir_dit_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ir_dit_patch_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ir_eps_to_x0": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),

@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "../../include/instarevive_b200.h"
@@ -26,16 +29,42 @@ void set_last_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static const bool on = [] {
-    const char* e = getenv("IR_NO_PDL");
+    const char* e = debug_env("IR_NO_PDL");
     return !(e && e[0] == '1');
   }();
   return on;
+}
+
+int ensure_smem_optin(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  IR_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({dev, kernel})) return IR_OK;
+  IR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({dev, kernel});
+  return IR_OK;
+}
+
+int device_num_sms() {
+  static std::atomic<int> sms[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 struct ProfRec {
   cudaEvent_t a, b;
   int klass;
   double flops;
+  int M, N, K;
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -46,13 +75,16 @@ void prof_before(cudaStream_t s) {
   cudaEventCreate(&g_prof_pending);
   cudaEventRecord(g_prof_pending, s);
 }
-void prof_after(cudaStream_t s, int klass, double flops) {
+void prof_after(cudaStream_t s, int klass, double flops, int M, int N, int K) {
   ProfRec r;
   r.a = g_prof_pending;
   cudaEventCreate(&r.b);
   cudaEventRecord(r.b, s);
   r.klass = klass;
   r.flops = flops;
+  r.M = M;
+  r.N = N;
+  r.K = K;
   g_prof.push_back(r);
 }
 
@@ -76,6 +108,26 @@ long long ir_launch_count(void) { return g_launches.load(std::memory_order_relax
 void ir_profile_begin(void) {
   g_prof.clear();
   g_prof_on = true;
+}
+
+long long ir_profile_records(int* klass, int* M, int* N, int* K, float* ms, long long cap) {
+  // per-launch records of the current profile pass in launch order (call between begin and end, after the work was
+  // enqueued); synchronises the device. Returns the number of records (may exceed cap: only cap are written).
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  long long i = 0;
+  for (const ProfRec& r : g_prof) {
+    if (i < cap) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      if (klass) klass[i] = r.klass;
+      if (M) M[i] = r.M;
+      if (N) N[i] = r.N;
+      if (K) K[i] = r.K;
+      if (ms) ms[i] = t;
+    }
+    ++i;
+  }
+  return i;
 }
 
 int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launches_by_class) {
@@ -162,6 +214,14 @@ int ir_dit_load_param(ir_dit* h, const char* name, const float* src_dev, long lo
 
 size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l) {
   return h ? dit_workspace_bytes(h->d, B, H, W, sum_l) : 0;
+}
+
+int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l) {
+  if (!h) {
+    set_last_error("ir_dit_reserve: null handle");
+    return IR_ERR_INVALID;
+  }
+  return dit_reserve(h->d, max_tokens, max_sum_l);
 }
 
 int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* timestep, const float* y,

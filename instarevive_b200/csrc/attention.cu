@@ -268,18 +268,14 @@ static int launch_attn(AttnDev p, int B, int heads, double flops, cudaStream_t s
   constexpr int BQ = NWARPS * 16;
   constexpr int smem = (2 * BQ + 4 * BKV) * LDS * 2;
   auto kern = flash_attn_kernel<NWARPS>;
-  static bool configured = false;
-  if (!configured) {
-    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  IR_TRY(ensure_smem_optin((const void*)kern, smem));
   // One resident wave when possible: the kernel is latency-bound (load -> compute -> store per query tile), so a CTA
   // walks QT consecutive query tiles of its (sample, head) with the next Q tile prefetched under the current one
   // instead of leaving the tail of the grid to a second, mostly empty wave.
   const int n_qtiles = (p.Tq + BQ - 1) / BQ;
   const long total = (long)n_qtiles * heads * B;
   const long slots = (long)device_num_sms() * (NWARPS == 8 ? 2 : 3);   // resident CTAs (registers / shared memory)
-  static const int forced_qt = [] { const char* e = getenv("IR_XATTN_QT"); return e ? atoi(e) : 0; }();
+  static const int forced_qt = [] { const char* e = debug_env("IR_XATTN_QT"); return e ? atoi(e) : 0; }();
   int qt = (int)((total + slots - 1) / slots);
   qt = qt < 1 ? 1 : (qt > 4 ? 4 : qt);
   if (forced_qt > 0) qt = forced_qt;

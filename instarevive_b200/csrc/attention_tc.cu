@@ -506,31 +506,20 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   // share of the exponentials evaluated on the FMA pipe: EMU8 of every 8 key pairs. 2 (25 %) balances the MUFU and
   // issue-slot budgets of the softmax warps; IR_ATTN_EMU overrides it for measurements (tools/gpu_attn_probe.py).
   static const int emu = [] {
-    const char* e = getenv("IR_ATTN_EMU");
+    const char* e = debug_env("IR_ATTN_EMU");
     const int v = e ? atoi(e) : 2;
     return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();
   auto launch = [&](auto kernel) -> int {
-    // every instantiation has the same function-pointer type, so the opt-in shared-memory size is tracked per pointer
-    static const void* configured[16] = {};
-    bool done = false;
-    int free_slot = -1;
-    for (int i = 0; i < 16; ++i) {
-      if (configured[i] == (const void*)kernel) done = true;
-      if (!configured[i] && free_slot < 0) free_slot = i;
-    }
-    if (!done) {
-      IR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      if (free_slot >= 0) configured[free_slot] = (const void*)kernel;
-    }
+    IR_TRY(ensure_smem_optin((const void*)kernel, SMEM_BYTES));
     const bool prof = prof_enabled();
     if (prof) prof_before(stream);
     IR_CUDA_CHECK(launch_pdl(kernel, grid, dim3(NTHREADS), SMEM_BYTES, stream, mk64, mk16, mvt, p));
-    if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD);
+    if (prof) prof_after(stream, PROF_ATTN, 4.0 * a.B * a.H * (double)a.T * a.T * HD, a.B * a.H, a.T, HD);
     return IR_OK;
   };
   static const int order = [] {
-    const char* e = getenv("IR_ATTN_ORDER");
+    const char* e = debug_env("IR_ATTN_ORDER");
     const int v = e ? atoi(e) : 3;
     return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();

@@ -22,6 +22,8 @@ FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
+if os.environ.get("IR_DEBUG") == "1":   # experiment build: the library honours the IR_* A/B environment switches
+    FLAGS.append("-DIR_DEBUG")
 
 
 def _digest(paths) -> str:

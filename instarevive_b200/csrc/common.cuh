@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define IR_DEVINL __device__ __forceinline__
 
@@ -47,6 +48,23 @@ enum {
   } while (0)
 
 void set_last_error(const char* fmt, ...);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: the opt-in is tracked per
+// (device, kernel) so that one process may drive several GPUs (api.cu).
+int ensure_smem_optin(const void* kernel, int bytes);
+int device_num_sms();   // SM count of the current device (cached per device)
+
+// Experiment / A-B switches (IR_ATTN_LEGACY, IR_GEMM_NOMMA, IR_GEMM_CFG, IR_CONV_WRES, ...) are read from the environment
+// ONLY in builds made with -DIR_DEBUG (IR_DEBUG=1 python -m instarevive_b200.csrc.build); the release library that ships
+// and is benchmarked ignores them, so no environment variable can route the product onto a legacy or garbage path.
+static inline const char* debug_env(const char* name) {
+#ifdef IR_DEBUG
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 // ---------------------------------------------------------------- small utilities
 IR_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -292,7 +292,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
   // x = x + gate_msa * attn(modulate(norm1(x)))
   IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 0 * D, mod + 1 * D, 6 * D, M, T, D, c.s));
   static const bool legacy_attn = [] {
-    const char* e = getenv("IR_ATTN_LEGACY");  // debugging aid: A/B against the mma.sync kernel
+    const char* e = debug_env("IR_ATTN_LEGACY");  // debugging aid: A/B against the mma.sync kernel
     return e && e[0] == '1';
   }();
   if (!legacy_attn) {
@@ -367,17 +367,52 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
   return IR_OK;
 }
 
-// position table, cached per token grid (the reference recomputes it on the host with numpy on every call)
+// position table, cached per token grid (the reference recomputes it on the host with numpy on every call). The
+// buffer is grow-only: a new grid that fits the current capacity only re-runs the (tiny) table kernel, so steady-state
+// forwards -- including alternating grids -- never call cudaMalloc / cudaFree (which synchronise the device).
 static int ensure_pos(Dit* d, int gh, int gw, cudaStream_t s) {
   if (d->pos_gh == gh && d->pos_gw == gw) return IR_OK;
   const int D = d->cfg.hidden;
-  if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
-  d->pos = nullptr;
-  d->pos_gh = d->pos_gw = 0;
-  IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)gh * gw * D * sizeof(float)));
+  const long need = (long)gh * gw * D;
+  if (need > d->pos_cap) {
+    if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
+    d->pos = nullptr;
+    d->pos_cap = 0;
+    d->pos_gh = d->pos_gw = 0;
+    IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)need * sizeof(float)));
+    d->pos_cap = need;
+  }
   IR_TRY(pos_embed_launch(d->pos, gh, gw, D, d->cfg.base_size, d->cfg.pe_interpolation, s));
   d->pos_gh = gh;
   d->pos_gw = gw;
+  return IR_OK;
+}
+
+// caption K/V cache [nblk][sumL][2D], grow-only
+static int ensure_ykv(Dit* d, int sumL) {
+  const long need_kv = (long)d->nblk * sumL * 2 * d->cfg.hidden;
+  if (need_kv <= d->ykv_cap) return IR_OK;
+  if (d->ykv) IR_CUDA_CHECK(cudaFree(d->ykv));
+  d->ykv = nullptr;
+  d->ykv_cap = 0;
+  d->ykv_sumL = -1;
+  IR_CUDA_CHECK(cudaMalloc(&d->ykv, (size_t)need_kv * sizeof(bf16)));
+  d->ykv_cap = need_kv;
+  return IR_OK;
+}
+
+int dit_reserve(Dit* d, int max_tokens, int max_sum_l) {
+  IR_REQUIRE(max_tokens >= 0 && max_sum_l >= 0, "dit_reserve: negative size");
+  const long need = (long)max_tokens * d->cfg.hidden;
+  if (need > d->pos_cap) {
+    if (d->pos) IR_CUDA_CHECK(cudaFree(d->pos));
+    d->pos = nullptr;
+    d->pos_cap = 0;
+    d->pos_gh = d->pos_gw = 0;
+    IR_CUDA_CHECK(cudaMalloc(&d->pos, (size_t)need * sizeof(float)));
+    d->pos_cap = need;
+  }
+  if (max_sum_l > 0) IR_TRY(ensure_ykv(d, max_sum_l));
   return IR_OK;
 }
 
@@ -444,14 +479,7 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   // ---- caption: y_embedder on the valid tokens, then K/V projections of all blocks in one batched GEMM
   if (!a.reuse_caption || d->ykv_sumL != a.sumL) {
     IR_REQUIRE(a.y && a.y_index, "dit_forward: caption embeddings missing");
-    const long need_kv = (long)d->nblk * a.sumL * 2 * D;
-    if (need_kv > d->ykv_cap) {
-      if (d->ykv) IR_CUDA_CHECK(cudaFree(d->ykv));
-      d->ykv = nullptr;
-      d->ykv_cap = 0;
-      IR_CUDA_CHECK(cudaMalloc(&d->ykv, (size_t)need_kv * sizeof(bf16)));
-      d->ykv_cap = need_kv;
-    }
+    IR_TRY(ensure_ykv(d, a.sumL));
     IR_TRY(gather_rows_launch(a.y, a.y_index, c.w.yg, a.sumL, d->cfg.caption_ch, s));
     GemmArgs g1;
     g1.A = c.w.yg; g1.lda = d->cfg.caption_ch; g1.W = d->y_fc1; g1.ldw = d->cfg.caption_ch;

@@ -67,7 +67,8 @@ struct Dit {
   const float *fin_table, *fin_w, *fin_b;
 
   // caches owned by the handle
-  float* pos = nullptr;  // (gh*gw, D) table for the last (gh, gw)
+  float* pos = nullptr;  // (gh*gw, D) table for the last (gh, gw); grow-only buffer
+  long pos_cap = 0;      // capacity in elements
   int pos_gh = 0, pos_gw = 0;
   bf16* ykv = nullptr;   // [nblk][sumL][2D] caption K/V of the last caption
   long ykv_cap = 0;      // capacity in elements
@@ -97,6 +98,9 @@ struct DitForwardArgs {
 };
 
 int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s);
+// pre-size the handle-owned caches (position table for up to max_tokens tokens, caption K/V for up to max_sum_l packed
+// caption tokens) so that no forward allocates
+int dit_reserve(Dit* d, int max_tokens, int max_sum_l);
 int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, cudaStream_t s);
 
 }  // namespace ir

@@ -712,25 +712,14 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   return make_tensor_map(m, base, rank, dims, strides_bytes, box, 128);
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
-int device_num_sms() { return num_sms(); }
+static int num_sms() { return device_num_sms(); }
 int gemm_conv_tiles_per_image(int H, int W) { return ((W + CONV_BW - 1) / CONV_BW) * ((H + CONV_BH - 1) / CONV_BH); }
 
 static bool conv_wres_enabled() {
   static const bool on = [] {
     // Opt-in ("1"): measured neutral on B200 (interleaved A/B at 1024^2: 24.41 vs 24.30 ms; conv class 7.57 vs 7.57 ms), so
     // the full-resolution N = 128 convs are NOT bound by re-streaming their weights; kept for experiments.
-    const char* e = getenv("IR_CONV_WRES");
+    const char* e = debug_env("IR_CONV_WRES");
     return e && e[0] == '1';
   }();
   return on;
@@ -741,11 +730,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
   using Cfg = GemmCfg<BN, CG, CONV>;
   constexpr int SMEM_MAX = 227 * 1024;
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
-  static bool configured = false;
-  if (!configured) {
-    IR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV ? SMEM_MAX : Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  IR_TRY(ensure_smem_optin((const void*)kern, CONV ? SMEM_MAX : Cfg::SMEM_BYTES));
   GemmDev p = p_in;
   const int slots = num_sms() / CG;
   int smem_bytes = Cfg::SMEM_BYTES;
@@ -782,7 +767,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
   IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
-  if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch));
+  if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch), p.M * (CONV ? 1 : p.batch), p.N, p.K);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;
@@ -814,7 +799,7 @@ struct TileCfg {
 static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int k_steps, int forced, bool conv) {
   static int env_cg = -1, env_bn = 0;
   if (env_cg < 0) {
-    const char* e = getenv("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
+    const char* e = debug_env("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
     env_cg = 0;
     if (e) sscanf(e, "%d,%d", &env_cg, &env_bn);
   }
@@ -879,7 +864,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.stride_bias = a.conv ? 0 : a.stride_bias;
   p.a_shared = (!a.conv && a.batch > 1 && a.strideA == 0) ? 1 : 0;
   {
-    static const int nomma = [] { const char* e = getenv("IR_GEMM_NOMMA"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int nomma = [] { const char* e = debug_env("IR_GEMM_NOMMA"); return (e && e[0] == '1') ? 1 : 0; }();
     p.dbg_nomma = nomma;
   }
   p.gelu_erf = a.gelu_erf;

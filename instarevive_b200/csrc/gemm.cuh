@@ -107,6 +107,6 @@ void count_launch(int n = 1);
 enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_XATTN = 3, PROF_NUM = 8 };   // ATTN: tcgen05 self-attention; XATTN: var-len cross-attention
 bool prof_enabled();
 void prof_before(cudaStream_t s);
-void prof_after(cudaStream_t s, int klass, double flops);
+void prof_after(cudaStream_t s, int klass, double flops, int M = 0, int N = 0, int K = 0);
 
 }  // namespace ir

@@ -1065,7 +1065,7 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
       C = Cout;
     }
     static const bool legacy_upconv = [] {
-      const char* e = getenv("IR_VAE_UPCONV_LEGACY");   // debugging aid: A/B against upsample2x + 3x3 conv
+      const char* e = debug_env("IR_VAE_UPCONV_LEGACY");   // debugging aid: A/B against upsample2x + 3x3 conv
       return e && e[0] == '1';
     }();
     if (lvl != 0 && !legacy_upconv) {
@@ -1091,7 +1091,7 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
   bf16* hn = c.w.buf[(cur + 1) & 3];
   IR_TRY(group_norm(c, d + ".norm_out", c.w.buf[cur], hn, H * W, C, true));
   static const bool legacy_conv_out = [] {
-    const char* e = getenv("IR_VAE_CONVOUT_LEGACY");   // debugging aid: A/B against the CUDA-core kernel
+    const char* e = debug_env("IR_VAE_CONVOUT_LEGACY");   // debugging aid: A/B against the CUDA-core kernel
     return e && e[0] == '1';
   }();
   if (!legacy_conv_out) {
@@ -1120,11 +1120,7 @@ int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in
   IR_REQUIRE(C == 128, "vae_decode: conv_out kernel is specialised for 128 input channels (got %d)", C);
   {
     constexpr int smem = (10 * 34) * (128 + 8) * 2 + 3 * 9 * 128 * 4;
-    static bool configured = false;
-    if (!configured) {
-      IR_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
-    }
+    IR_TRY(ensure_smem_optin((const void*)conv_out_kernel<128>, smem));
     conv_out_kernel<128><<<dim3(div_up_l(W, 32), div_up_l(H, 8), B), 256, smem, s>>>(
         hn, vp<float>(v, d + ".conv_out.weight"), vp<float>(v, d + ".conv_out.bias"), out, H, W, out_scale, out_shift);
     IR_CUDA_CHECK(cudaGetLastError());

@@ -82,8 +82,11 @@ def _micro_conditions(B: int, h: int, w: int, device):
 
 
 def generate_sample_1step(model, scheduler, latents, maxt, prompt_embeds, prompt_attention_masks=None, c=None,
-                          use_control: bool = True):
-    """generate.py:22-42: one forward at t = maxt, eps -> x0. With use_control the degraded latent is also the control."""
+                          use_control: bool = False):
+    """generate.py:22-42: one forward at t = maxt, eps -> x0. c=None runs the plain 28-block path, exactly as in the
+    reference (pixart_controlnet.py:245-247; every reference caller passes no c). use_control=True (keyword-only
+    extension, the north-star configuration) feeds the degraded latent itself to the ControlNet-Half branch: c = latents,
+    the authors' own ControlNet usage (test_scripts/test_controlnet.py:137-139)."""
     t = torch.full((1,), maxt, device=latents.device).long()
     if c is None and use_control and getattr(model, "copy_blocks_num", 0) > 0:
         c = latents

@@ -285,9 +285,14 @@ class ControlPixArtMSHalf(nn.Module):
         """Packing of the valid caption tokens (pixart_controlnet.py:221-231): returns device int32 tables
         (y_index, kv_off, kv_len), sum_l and whether the cached caption K/V can be reused. One host sync when the
         caption changes (the reference pays `mask.sum().tolist()` on every call)."""
-        key = (y.data_ptr(), y._version, tuple(y.shape), None if mask is None else (mask.data_ptr(), mask._version, tuple(mask.shape)), bs)
-        if key == self._cap_key:
+        # The cache entry HOLDS the caption and mask tensors it was computed from and is hit only by the very same tensor
+        # objects at an unchanged in-place version. (Keying on data_ptr alone is unsafe: the caching allocator hands a
+        # freed caption's address to the next tensor of the same shape, whose _version starts at 0 again.)
+        ref = self._cap_key
+        if (ref is not None and ref[0] is y and ref[1] == y._version and ref[2] is mask
+                and (mask is None or ref[3] == mask._version) and ref[4] == bs):
             return self._cap_tensors + (True,)
+        key = (y, y._version, mask, None if mask is None else mask._version, bs)
         ny, lmax = y.shape[0], y.shape[2]
         if mask is not None:
             m = mask
@@ -352,9 +357,6 @@ class ControlPixArtMSHalf(nn.Module):
         hw, ar = hw.contiguous(), ar.contiguous()
         if y.dim() != 4 or y.shape[1] != 1 or y.shape[3] != self.caption_channels:
             raise ValueError(f"y must be (N,1,L,{self.caption_channels}), got {tuple(y.shape)}")
-        if yy.data_ptr() != y.data_ptr():
-            # keep the caption cache keyed on the caller's tensor, not on the fp32 copy
-            pass
         y_index, kv_off, kv_len, sum_l, reuse = self._caption_tables(y, mask, bs)
         out = torch.empty(bs, self.out_channels, H, W, **f32)
         with torch.cuda.device(dev):

@@ -154,18 +154,56 @@ def _scheduler():
 
 
 # ------------------------------------------------------------------------------------------------ restoration core
+class PhaseTimer:
+    """CUDA events at the phase boundaries of a tiled restore (bench.py's per-phase report). `mark(name)` closes the
+    phase `name`; `summary()` (after a synchronize) returns {phase: ms} summed over the recorded steps."""
+
+    def __init__(self):
+        self.steps = []
+        self._cur = None
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._cur = [("", ev)]
+        self.steps.append(self._cur)
+
+    def mark(self, name: str):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._cur.append((name, ev))
+
+    def summary(self):
+        out = {}
+        for st in self.steps:
+            for (_, a), (name, b) in zip(st[:-1], st[1:]):
+                out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def _mark(timer, name):
+    if timer is not None:
+        timer.mark(name)
+
+
 @torch.no_grad()
 def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor, y, y_mask, *, tiled: bool,
                     tile_size: int = 512, tile_stride: int = 448, color_fix_type: str = "wavelet", scheduler=None,
-                    decode_batch: int = 8, group=None, return_latents: bool = False, distributed: bool = True):
+                    decode_batch: int = 8, group=None, return_latents: bool = False, distributed: bool = True,
+                    use_control: bool = False, timer: Optional[PhaseTimer] = None):
     """Everything of process() between VAE-encode and the uint8 conversion (inference.py:111-153), on the GPU.
-    control: (N,3,H,W) in [0,1]; init_noise: (N,4,H/8,W/8). Returns the fp32 image buffer (N,3,H,W) [and latents]."""
+    control: (N,3,H,W) in [0,1]; init_noise: (N,4,H/8,W/8). Returns the fp32 image buffer (N,3,H,W) [and latents].
+    use_control=False (default) is the reference's literal call, generate_sample_1step(model, ..., c=None)
+    (inference.py:114,131); True feeds the degraded latent to the ControlNet branch as well (north-star configuration)."""
     scheduler = scheduler or _scheduler()
     sf = float(vae.config.scaling_factor)
     n, _, height, width = control.shape
     h, w = height // 8, width // 8
+    if timer is not None:
+        timer.begin()
     if not tiled:
-        latents = generate_sample_1step(model, scheduler, init_noise, 400, y, y_mask)
+        latents = generate_sample_1step(model, scheduler, init_noise, 400, y, y_mask, use_control=use_control)
+        _mark(timer, "dit")
         # big batches are decoded in chunks (bounded workspace; every image's result is independent of the batch
         # it is decoded in, so chunking is bit-neutral)
         chunk = max(16, decode_batch)
@@ -174,6 +212,7 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
         else:
             img = torch.cat([vae.decode_tensor(latents[i:i + chunk], in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)
                              for i in range(0, n, chunk)], dim=0)
+        _mark(timer, "decode")
         return (img, latents) if return_latents else img
 
     rank, world = _dist_info(group) if distributed else (0, 1)
@@ -187,13 +226,16 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
     if e > s:
         tiles_in = tile_gather(init_noise.contiguous(), mine, th, tw, 1)              # (k,N,4,th,tw)
         x0 = generate_sample_1step(model, scheduler, tiles_in.view(-1, 4, th, tw), 400, _tile_captions(y, n, e - s),
-                                   _tile_captions(y_mask, n, e - s))
+                                   _tile_captions(y_mask, n, e - s), use_control=use_control)
         x0 = x0.view(e - s, n, 4, th, tw)
     else:
         x0 = torch.empty(0, n, 4, th, tw, device=control.device)
+    _mark(timer, "dit")
     if world > 1:
         x0 = all_gather_items(x0, nt, group)                                          # all-gather #1: tile latents
+    _mark(timer, "allgather_latents")
     noise_buffer = tile_blend(x0, coords, h, w, 1)                                    # inference.py:133-136
+    _mark(timer, "latent_blend")
     # loop 2 (inference.py:139-152): decode + colour-fix my tiles, blend in pixel space
     outs = []
     # balanced decode chunks of at most decode_batch tiles (25 tiles -> 7+6+6+6 rather than 8+8+8+1: a lone tile would
@@ -210,9 +252,12 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
             ti = wavelet_reconstruction(ti, cond) if color_fix_type == "wavelet" else adaptive_instance_normalization(ti, cond)
         outs.append(ti.view(b1 - b0, n, 3, 8 * th, 8 * tw))
     tiles_px = torch.cat(outs, dim=0) if outs else torch.empty(0, n, 3, 8 * th, 8 * tw, device=control.device)
+    _mark(timer, "decode_colorfix")
     if world > 1:
         tiles_px = all_gather_items(tiles_px, nt, group)                              # all-gather #2: decoded tiles
+    _mark(timer, "allgather_pixels")
     img = tile_blend(tiles_px, coords, height, width, 8)                              # inference.py:151-153
+    _mark(timer, "pixel_blend")
     return (img, noise_buffer) if return_latents else img
 
 
@@ -226,10 +271,14 @@ def _tile_captions(t, n_samples: int, n_tiles: int):
 @torch.no_grad()
 def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fix_type: str,
             disable_preprocess_model: bool, tiled: bool, tile_size: int, tile_stride: int, preprocess_model=None,
-            vae=None, y=None, y_mask=None, *, scheduler=None, decode_batch: int = 8, group=None
-            ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+            vae=None, y=None, y_mask=None, *, scheduler=None, decode_batch: int = 8, group=None,
+            use_control: bool = False) -> Tuple[List[np.ndarray], List[np.ndarray]]:
     """Signature and semantics of the reference's process() (test_scripts/inference.py:56-166).
-    control_imgs: HWC uint8 RGB arrays of equal size (multiples of 64). Returns (preds, stage1_preds) as uint8 HWC."""
+    control_imgs: HWC uint8 RGB arrays of equal size (multiples of 64). Returns (preds, stage1_preds) as uint8 HWC.
+    use_control (keyword-only extension): False (default) reproduces the reference's literal call
+    `generate_sample_1step(model, ..., y, y_mask)` with c=None, i.e. the plain 28-block path (inference.py:114,131);
+    True feeds the degraded latent to the ControlNet-Half branch too (c = latents: the north-star configuration, what
+    the goldens, the benchmark and scripts/inference.py with a ControlNet checkpoint exercise)."""
     device = model.device
     n_samples = len(control_imgs)
     # reference: torch.tensor(np.stack(imgs) / 255.0, dtype=float32) on the host (inference.py:92); here the uint8 image
@@ -247,6 +296,6 @@ def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fi
     init_noise = c_latent * vae.config.scaling_factor
     img = restore_latents(model, vae, control, init_noise, y, y_mask, tiled=tiled, tile_size=tile_size,
                           tile_stride=tile_stride, color_fix_type=color_fix_type, scheduler=scheduler,
-                          decode_batch=decode_batch, group=group)
+                          decode_batch=decode_batch, group=group, use_control=use_control)
     x_samples, stage1 = _to_host_pair(to_uint8_nhwc(img), to_uint8_nhwc(control))
     return [x_samples[i] for i in range(n_samples)], [stage1[i] for i in range(n_samples)]

@@ -192,7 +192,10 @@ def main() -> None:
             preds, stage1_preds = ir.process(
                 model, [x], strength=1, color_fix_type=args.color_fix_type, disable_preprocess_model=disable_pre,
                 tiled=args.tiled, tile_size=args.tile_size, tile_stride=args.tile_stride, vae=vae,
-                preprocess_model=preprocess_model, y=y, y_mask=y_mask)
+                preprocess_model=preprocess_model, y=y, y_mask=y_mask,
+                # a checkpoint that carries a ControlNet-Half branch is run WITH it (c = degraded latent); a plain
+                # generator checkpoint takes the reference's literal c=None path (inference.py:114,131)
+                use_control=getattr(model, "copy_blocks_num", 0) > 0)
             pred, stage1_pred = preds[0], stage1_preds[0]
             if not args.use_center_crop:  # remove padding
                 pred = pred[:lq_resized.height, :lq_resized.width, :]

@@ -79,7 +79,7 @@ def test_dit_full_model_matches_reference_golden(golden_dir):
     assert err_eps <= LATENT_TOL and err_all <= LATENT_TOL, (err_eps, err_all)
     # one-step x0 through the reference-named host functions; the eps error is amplified by sqrt(1-abar)/sqrt(abar)=2.04
     x, ts, y, mask, info = weights.make_inputs(1, 64, 64, seed=0, lens=(77,))
-    x0 = ir.generate_sample_1step(net, ir.DDPMSchedulerLite(), x.to(dev), 400, y.to(dev), mask.to(dev)).cpu()
+    x0 = ir.generate_sample_1step(net, ir.DDPMSchedulerLite(), x.to(dev), 400, y.to(dev), mask.to(dev), use_control=True).cpu()
     gx = torch.from_numpy(np.load(golden_dir / "x0_full_b1_64x64.npz")["x0"])
     assert (x0 - gx).abs().max().item() <= 2.1 * LATENT_TOL
     # batch invariance (tiles of one image are batched): sample 0 of a batch of 3 equals the batch-1 result bit for bit
@@ -87,6 +87,36 @@ def test_dit_full_model_matches_reference_golden(golden_dir):
     info3 = {k: v.to(dev).repeat(3, 1) for k, v in info.items()}
     out3 = net(xb, ts.to(dev).expand(3), y.to(dev), mask=mask.to(dev), data_info=info3, c=xb).cpu()
     assert torch.equal(out3[:1], out)
+
+
+def test_caption_cache_honours_a_new_caption_at_a_recycled_address(small_model):
+    """The caption table / K/V cache (nets._caption_tables) must miss when a NEW caption tensor lands on the address of a
+    freed one (the caching allocator recycles same-shaped blocks; a fresh tensor's _version is 0 again), when the caption
+    is modified in place, and must hit (bit-identical output) when the very same tensor is passed again."""
+    from instarevive_b200 import weights
+    dev = _cuda()
+    x, ts, y1, mask, info = weights.make_inputs(1, 32, 32, seed=0, lens=(77,))
+    _, _, y2, _, _ = weights.make_inputs(1, 32, 32, seed=1, lens=(77,))
+    info = {k: v.to(dev) for k, v in info.items()}
+    xd, td, md = x.to(dev), ts.to(dev), mask.to(dev)
+
+    def run(y):
+        return small_model(xd, td, y, mask=md, data_info=info, c=xd).cpu()
+
+    ya = y1.to(dev)
+    addr = ya.data_ptr()
+    out1 = run(ya)
+    assert torch.equal(run(ya), out1)               # cache hit
+    del ya
+    yb = y2.to(dev)                                 # same shape: the allocator hands back the freed block
+    recycled = yb.data_ptr() == addr
+    out2 = run(yb)
+    small_model._cap_key = None                     # reference result for caption 2 with the cache dropped
+    ref2 = run(yb)
+    assert torch.equal(out2, ref2), f"stale caption K/V (address recycled: {recycled})"
+    assert not torch.equal(out2, out1)
+    yb.copy_(y1.to(dev))                            # in-place change of the cached tensor
+    assert torch.equal(run(yb), out1)
 
 
 def test_pos_embed_and_forward_c(small_model, golden_dir):
@@ -247,7 +277,7 @@ def test_process_matches_reference_golden(vae_dec, golden_dir, tag):
     img = weights.synthetic_degraded_image(int(g["H"]), int(g["W"]), seed=int(g["img_seed"]))
     preds, stage1 = ir.process(net, [img], strength=1, color_fix_type=str(g["fix"]), disable_preprocess_model=True,
                                tiled=bool(g["tiled"]), tile_size=512, tile_stride=448, vae=vae_dec, y=y.to(dev),
-                               y_mask=mask.to(dev))
+                               y_mask=mask.to(dev), use_control=True)
     assert preds[0].shape == g["pred"].shape and preds[0].dtype == np.uint8
     np.testing.assert_array_equal(stage1[0], img)
     p = psnr(preds[0], g["pred"], 255.0)
@@ -268,7 +298,7 @@ def test_tiled_restore_sharding_is_bit_identical(vae_dec):
     H = W = 1024  # 9 tiles of 512 px
     control = torch.from_numpy(weights.synthetic_degraded_image(H, W, seed=5)).to(dev).float().div(255).permute(2, 0, 1)[None]
     init = weights.SyntheticVAE(None).encode(control * 2 - 1).latent_dist.mode() * 0.18215
-    full, lat = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, return_latents=True)
+    full, lat = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, return_latents=True, use_control=True)
     windows = pipeline._sliding_windows(128, 128, 64, 56)
     assert len(windows) == 9
     coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=dev)
@@ -277,12 +307,12 @@ def test_tiled_restore_sharding_is_bit_identical(vae_dec):
     for r in range(4):  # emulate 4 ranks: 3,2,2,2 tiles
         s, e = pipeline.shard_range(9, r, 4)
         tin = pipeline.tile_gather(init.contiguous(), coords[s:e].contiguous(), 64, 64, 1)
-        parts.append(ir.generate_sample_1step(net, sched, tin.view(-1, 4, 64, 64), 400, y, mask).view(e - s, 1, 4, 64, 64))
+        parts.append(ir.generate_sample_1step(net, sched, tin.view(-1, 4, 64, 64), 400, y, mask, use_control=True).view(e - s, 1, 4, 64, 64))
     lat2 = pipeline.tile_blend(torch.cat(parts), coords, 128, 128, 1)
     assert torch.equal(lat2, lat)
     # pixel space: decoding the tiles in differently sized batches (what differently sized shards do) is bit-identical
-    full3 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=3)
-    full1 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=1)
+    full3 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=3, use_control=True)
+    full1 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=True, decode_batch=1, use_control=True)
     assert torch.equal(full3, full) and torch.equal(full1, full)
     assert full.shape == (1, 3, H, W) and torch.isfinite(full).all()
     assert float(full.min()) > -0.5 and float(full.max()) < 1.5
@@ -344,14 +374,14 @@ def test_full_size_properties_1024(vae_dec):
     enc = weights.SyntheticVAE(None)
     init = (enc.encode(control * 2 - 1).latent_dist.mode() * 0.18215).contiguous()
     sched = ir.DDPMSchedulerLite()
-    a, lat_a = pipeline.restore_latents(net, vae_dec, control[:1], init[:1], y, mask, tiled=False, scheduler=sched, return_latents=True)
-    b, lat_b = pipeline.restore_latents(net, vae_dec, control[:1], init[:1], y, mask, tiled=False, scheduler=sched, return_latents=True)
+    a, lat_a = pipeline.restore_latents(net, vae_dec, control[:1], init[:1], y, mask, tiled=False, scheduler=sched, return_latents=True, use_control=True)
+    b, lat_b = pipeline.restore_latents(net, vae_dec, control[:1], init[:1], y, mask, tiled=False, scheduler=sched, return_latents=True, use_control=True)
     assert torch.equal(a, b) and torch.equal(lat_a, lat_b)                                   # (i)
-    both, lat2 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=False, scheduler=sched, return_latents=True)
+    both, lat2 = pipeline.restore_latents(net, vae_dec, control, init, y, mask, tiled=False, scheduler=sched, return_latents=True, use_control=True)
     assert torch.equal(lat2[:1], lat_a) and torch.equal(both[:1], a)                         # (ii)
     assert not torch.equal(both[1:], a)
     one_tile = pipeline.restore_latents(net, vae_dec, control[:1], init[:1], y, mask, tiled=True, tile_size=1024, tile_stride=896,
-                                        color_fix_type="none", scheduler=sched)
+                                        color_fix_type="none", scheduler=sched, use_control=True)
     assert torch.equal(one_tile, a)                                                          # (iii)
     x = init[:1]
     mo = torch.randn(1, 8, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(0))

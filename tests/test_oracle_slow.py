@@ -42,3 +42,27 @@ def test_process_matches_reference_loop(golden_dir):
         diff = np.abs(pred[0].astype(np.int32) - g["pred"].astype(np.int32))
         assert diff.max() <= 1, (tag, diff.max())          # fp32 summation-order noise can flip a truncation
         assert (diff > 0).mean() < 1e-3
+
+
+def test_dit_oracle_full_model_1024(golden_dir):
+    """The oracle port at the benchmark's own size (128x128 latent, T = 4096): pins the restatement that bench.py's
+    reference arm / cpu_baseline leg times at 1024x1024 to the unmodified reference's output."""
+    g = np.load(golden_dir / "dit_full_b1_128x128.npz")
+    sd = weights.make_dit_state_dict(depth=28, copy_blocks=13, seed=1)
+    x, ts, y, mask, info = weights.make_inputs(1, 128, 128, seed=0, lens=(77,))
+    out = dit_oracle.control_pixart_forward(sd, x, ts, y, mask, info, c=x.clone())
+    assert (out - torch.from_numpy(g["out"])).abs().max().item() < 5e-4
+    x0 = dit_oracle.eps_to_mu(out.chunk(2, dim=1)[0], x, 400)
+    assert (x0 - torch.from_numpy(g["x0"])).abs().max().item() < 2e-3
+
+
+def test_vae_oracle_1024(golden_dir):
+    """Decoder oracle at a 128x128 latent (mid-attention over 16384 tokens) vs the reference Decoder's crops / block means."""
+    g = np.load(golden_dir / "vae_b1_128x128.npz")
+    sd = weights.make_vae_decoder_state_dict(seed=2)
+    z = torch.randn(1, 4, 128, 128, generator=torch.Generator().manual_seed(8)) / 0.18215 * 0.6
+    img = vae_oracle.vae_decode(sd, z)
+    for (y0, x0), ref in zip(g["crop_origins"], g["crops"]):
+        assert (img[0, :, y0:y0 + 128, x0:x0 + 128] - torch.from_numpy(ref)).abs().max().item() < 2e-4
+    means = img.reshape(1, 3, 128, 8, 128, 8).mean(dim=(3, 5))
+    assert (means - torch.from_numpy(g["means"])).abs().max().item() < 1e-4

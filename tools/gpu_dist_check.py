@@ -23,8 +23,8 @@ init = (weights.SyntheticVAE(None).encode(control * 2 - 1).latent_dist.mode() * 
 g = [torch.empty_like(init) for _ in range(dist.get_world_size())]
 dist.all_gather(g, init)
 print(f"rank {rank}: init identical across ranks: {all(torch.equal(g[0], t) for t in g)} max diff {max((g[0]-t).abs().max().item() for t in g)}", flush=True)
-img_d, lat_d = pipeline.restore_latents(net, vae, control, init, y, mask, tiled=True, return_latents=True)
-img_l, lat_l = pipeline.restore_latents(net, vae, control, init, y, mask, tiled=True, return_latents=True, distributed=False)
+img_d, lat_d = pipeline.restore_latents(net, vae, control, init, y, mask, tiled=True, return_latents=True, use_control=True)
+img_l, lat_l = pipeline.restore_latents(net, vae, control, init, y, mask, tiled=True, return_latents=True, distributed=False, use_control=True)
 torch.cuda.synchronize()
 print(f"rank {rank}: latents identical {torch.equal(lat_d, lat_l)} ({(lat_d-lat_l).abs().max().item():.3g}); "
       f"pixels identical {torch.equal(img_d, img_l)} ({(img_d-img_l).abs().max().item():.3g})", flush=True)

@@ -21,18 +21,18 @@ windows = pipeline._sliding_windows(256, 256, 64, 56)
 coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=dev)
 sched = ir.DDPMSchedulerLite()
 tin = pipeline.tile_gather(init, coords, 64, 64, 1).view(-1, 4, 64, 64)
-full = ir.generate_sample_1step(net, sched, tin, 400, y, mask)
-again = ir.generate_sample_1step(net, sched, tin, 400, y, mask)
+full = ir.generate_sample_1step(net, sched, tin, 400, y, mask, use_control=True)
+again = ir.generate_sample_1step(net, sched, tin, 400, y, mask, use_control=True)
 print("run-to-run identical (batch 25):", torch.equal(full, again))
-a = ir.generate_sample_1step(net, sched, tin[:13].contiguous(), 400, y, mask)
-b = ir.generate_sample_1step(net, sched, tin[13:].contiguous(), 400, y, mask)
+a = ir.generate_sample_1step(net, sched, tin[:13].contiguous(), 400, y, mask, use_control=True)
+b = ir.generate_sample_1step(net, sched, tin[13:].contiguous(), 400, y, mask, use_control=True)
 parts = torch.cat([a, b])
 print("25 vs 13+12 identical:", torch.equal(full, parts), "max diff", (full - parts).abs().max().item())
 for i in range(25):
     if not torch.equal(full[i], parts[i]):
         print("  tile", i, "differs, max", (full[i] - parts[i]).abs().max().item())
 for nb in (1, 5, 8, 12):
-    c = ir.generate_sample_1step(net, sched, tin[:nb].contiguous(), 400, y, mask)
+    c = ir.generate_sample_1step(net, sched, tin[:nb].contiguous(), 400, y, mask, use_control=True)
     print(f"batch {nb} prefix identical to batch-25 prefix:", torch.equal(c, full[:nb]))
 # VAE decode batch dependence on real latents
 lat = pipeline.tile_blend(full.view(25, 1, 4, 64, 64), coords, 256, 256, 1)
