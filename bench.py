@@ -321,6 +321,15 @@ def run_cuda(args):
         torch.cuda.synchronize()
         return zlib.crc32(pipeline.to_uint8_nhwc(img[:1]).cpu().numpy().tobytes())
 
+
+    if args.only_tiled:   # development aid: just the tiled_2048 block (strong scaling), one JSON line
+        blk = run_tiled_block(args, ir, pipeline, weights, net, vae, sched, y, mask, dev, world, rank, timed, crc_of, load_images)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "n_gpus": world, "tiled_2048": blk}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     # ================================================================== headline workload
     tiled = args.workload == "tiled"
     side = args.size
@@ -511,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true", help="skip the VAE-encoder / SwinIR side measurements and e2e_full_cli")
     ap.add_argument("--dump-shapes", default=None, help="write the per-launch shape list of one profiled step (JSON) here")
+    ap.add_argument("--only-tiled", action="store_true", help="development aid: run only the tiled_2048 block")
     ap.add_argument("--no-tiled", action="store_true", help="skip the tiled_2048 block (BASELINE configs[3])")
     args = ap.parse_args()
     if args.size is None:

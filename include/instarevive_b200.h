@@ -91,15 +91,17 @@ int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l);
 /*
  * x, c: (B,4,H,W) fp32 latents (c may be NULL: plain 28-block path); timestep: (B) fp32;
  * y: (rows,4096) fp32 caption embeddings; y_index: device int32 (sum_l) valid rows of y, sample-major;
- * kv_off / kv_len: device int32 (B) offsets / lengths into the packed caption rows;
+ * kv_off / kv_len: device int32 (B) offsets / lengths into the packed caption rows; max_l = max over samples of
+ * (kv_off % 8 + kv_len) (<= 384; the cross-attention key window, whose TMA box starts at the packed row rounded down to a
+ * multiple of 8), kv_total = sum over samples of kv_len (FLOP accounting) -- host copies;
  * img_hw: device fp32 (B,2); aspect: device fp32 (B); out: (B,8,H,W) fp32.
  * reuse_caption != 0 skips the caption embedding and the per-block K/V projections and reuses the ones cached by
  * the previous call on this handle (same captions, same sum_l).
  */
 int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* timestep, const float* y,
                    const int32_t* y_index, const int32_t* kv_off, const int32_t* kv_len, const float* img_hw,
-                   const float* aspect, float* out, int B, int H, int W, int sum_l, int reuse_caption,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   const float* aspect, float* out, int B, int H, int W, int sum_l, int max_l, long long kv_total,
+                   int reuse_caption, void* workspace, size_t workspace_bytes, void* stream);
 
 /* x0 = (x - sqrt(1-abar) * eps) / sqrt(abar); eps = channels [0,C) of model_out (B,2C,H,W). */
 int ir_eps_to_x0(const float* x, const float* model_out, float* x0, int B, int C, int HW, float sqrt_abar,
@@ -203,6 +205,15 @@ int ir_gemm_qkv_heads(const void* A, const void* W, const float* bias, int M, in
 /* tcgen05 self-attention on head-major operands (see ir_gemm_qkv_heads); out: (B*T, ldo) bf16. */
 int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* vt_heads, void* out, long long ldo, int B,
                          int H, int head_dim, int T, int Tp, float scale, void* stream);
+/* tcgen05 cross-attention to the packed caption (MultiHeadCrossAttention.forward, PixArt_blocks.py:43-58 with
+ * BlockDiagonalMask.from_seqlens([T]*B, y_lens)): q (B*T, ldq) bf16 head-interleaved; kv (sum_l, ldkv) bf16 = kv_linear
+ * output (K at columns [0, heads*hd), V at [heads*hd, 2*heads*hd)); sample b attends to rows [kv_off[b], +kv_len[b]);
+ * max_l >= every (kv_off[b] % 8 + kv_len[b]) (host copy, <= 384); vt_ws: device scratch of ir_cross_attention_vt_bytes(heads, sum_l) bytes
+ * that receives the transposed V half (inside ir_dit_forward this copy is made once per caption); out (B*T, ldo) bf16. */
+size_t ir_cross_attention_vt_bytes(int heads, int sum_l);
+int ir_cross_attention_tc_bf16(const void* q, const void* kv, void* vt_ws, void* out, long long ldq, long long ldkv,
+                               long long ldo, int B, int heads, int head_dim, int T, int sum_l, const int32_t* kv_off,
+                               const int32_t* kv_len, int max_l, float scale, void* stream);
 /* Diagnostics: with a device buffer of the returned length (int64 elements) set, ir_attention_tc_bf16 runs an
  * instrumented instantiation that records SM-clock stamps of the warp roles of CTA (0,0,0); NULL switches it off. */
 int ir_debug_attention_trace(long long* device_buf);

@@ -41,7 +41,7 @@ PROTOTYPES = {
     "ir_dit_load_param": (_i, [_vp, C.c_char_p, _vp, _ll, _vp]),
     "ir_dit_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ir_dit_reserve": (_i, [_vp, _i, _i]),
-    "ir_dit_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ir_dit_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp, _sz, _vp]),
     "ir_dit_patch_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ir_eps_to_x0": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "ir_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
@@ -50,6 +50,8 @@ PROTOTYPES = {
     "ir_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp]),
     "ir_gemm_qkv_heads": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "ir_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp]),
+    "ir_cross_attention_vt_bytes": (_sz, [_i, _i]),
+    "ir_cross_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),
     "ir_debug_attention_trace": (_i, [_vp]),
     "ir_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ir_pos_embed": (_i, [_vp, _i, _i, _i, _i, _f, _vp]),

@@ -226,8 +226,8 @@ int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l) {
 
 int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* timestep, const float* y,
                    const int32_t* y_index, const int32_t* kv_off, const int32_t* kv_len, const float* img_hw,
-                   const float* aspect, float* out, int B, int H, int W, int sum_l, int reuse_caption,
-                   void* workspace, size_t workspace_bytes, void* stream) {
+                   const float* aspect, float* out, int B, int H, int W, int sum_l, int max_l, long long kv_total,
+                   int reuse_caption, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) {
     set_last_error("ir_dit_forward: null handle");
     return IR_ERR_INVALID;
@@ -247,6 +247,8 @@ int ir_dit_forward(ir_dit* h, const float* x, const float* c, const float* times
   a.H = H;
   a.W = W;
   a.sumL = sum_l;
+  a.max_len = max_l;
+  a.kv_total = (long)kv_total;
   a.reuse_caption = reuse_caption;
   a.workspace = workspace;
   a.workspace_bytes = workspace_bytes;
@@ -513,6 +515,37 @@ int ir_attention_bf16(const void* q, const void* k, const void* v, void* out, lo
   a.kv_len = kv_len;
   a.scale = scale;
   return attention_launch(a, (cudaStream_t)stream);
+}
+
+size_t ir_cross_attention_vt_bytes(int heads, int sum_l) { return (size_t)xattention_vt_elems(heads, sum_l) * sizeof(bf16); }
+
+int ir_cross_attention_tc_bf16(const void* q, const void* kv, void* vt_ws, void* out, long long ldq, long long ldkv,
+                               long long ldo, int B, int heads, int head_dim, int T, int sum_l, const int32_t* kv_off,
+                               const int32_t* kv_len, int max_l, float scale, void* stream) {
+  if (!kv || !vt_ws) {
+    set_last_error("ir_cross_attention_tc_bf16: null kv / vt workspace");
+    return IR_ERR_INVALID;
+  }
+  IR_TRY(xattention_transpose_v((const bf16*)kv, (bf16*)vt_ws, 1, heads, sum_l, ldkv, (cudaStream_t)stream));
+  XAttnTcArgs a;
+  a.vt = (const bf16*)vt_ws;
+  a.q = (const bf16*)q;
+  a.kv = (const bf16*)kv;
+  a.out = (bf16*)out;
+  a.ldq = ldq;
+  a.ldkv = ldkv;
+  a.ldo = ldo;
+  a.B = B;
+  a.H = heads;
+  a.head_dim = head_dim;
+  a.T = T;
+  a.sumL = sum_l;
+  a.kv_off = kv_off;
+  a.kv_len = kv_len;
+  a.max_len = max_l;
+  a.kv_total = (long)B * max_l;
+  a.scale = scale;
+  return xattention_tc_launch(a, (cudaStream_t)stream);
 }
 
 int ir_gemm_qkv_heads(const void* A, const void* W, const float* bias, int M, int K, int T, int Tp, int H, int hd,

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "dit.cu", "vae.cu", "tiles.cu", "swinir.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "xattention_tc.cu", "elementwise.cu", "dit.cu", "vae.cu", "tiles.cu", "swinir.cu"]
 LIB = HERE / "libinstarevive_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -166,12 +166,27 @@ int dit_create(const DitConfig& cfg, Dit** out) {
   return IR_OK;
 }
 
+static bool dual_chain_enabled() {
+  static const bool on = [] {
+    const char* e = debug_env("IR_DIT_SINGLE_STREAM");   // A/B aid (debug builds only)
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 void dit_destroy(Dit* d) {
   if (!d) return;
+  if (d->side) {
+    cudaStreamSynchronize(d->side);
+    cudaStreamDestroy(d->side);
+    cudaEventDestroy(d->ev_fork);
+    for (auto& e : d->ev_c) cudaEventDestroy(e);
+  }
   cudaFree(d->wb);
   cudaFree(d->wf);
   cudaFree(d->pos);
   cudaFree(d->ykv);
+  cudaFree(d->ykv_t);
   delete d;
 }
 
@@ -217,11 +232,18 @@ struct Bump {
   }
 };
 
+// per-chain scratch: the base chain and the control chain run concurrently on two streams (see dit_forward)
+struct ChainWs {
+  bf16 *xq;                       // bf16 copy of the stream after the self-attention residual (cross-attn query input)
+  bf16 *xn, *att, *qc, *hm;       // LN+modulate output, attention output, cross-attn queries, MLP hidden
+  bf16 *qh, *kh, *vt;             // head-major q / k and transposed v for the tcgen05 attention kernel
+};
+
 struct DitWs {
   float *xs, *cs;                 // fp32 residual streams (base, control)
-  bf16 *xq, *cb;                  // bf16 copies (cross-attn query input / control stream for after_proj)
-  bf16 *xn, *qkv, *att, *qc, *hm; // per-block scratch
-  bf16 *qh, *kh, *vt;             // head-major q / k and transposed v for the tcgen05 attention kernel
+  ChainWs ch[2];                  // [0] base chain, [1] control chain
+  bf16* cb;                       // [copy_blocks][M][D] bf16 copies of the control stream c_1..c_n (after_proj inputs):
+                                  // one buffer per control block, because the control chain runs ahead of the base chain
   bf16* ctok;                     // patch-embedded control tokens (bf16, before_proj input)
   float *sin, *hid, *t, *t0, *mod;
   bf16 *yg, *yh, *ye;
@@ -229,21 +251,24 @@ struct DitWs {
 
 static size_t carve(const Dit* d, DitWs& w, void* base, int B, int H, int W, int sumL) {
   const long D = d->cfg.hidden, Dm = D * d->cfg.mlp_ratio;
-  const long M = (long)B * (H / 2) * (W / 2);
+  const long T = (long)(H / 2) * (W / 2);
+  const long M = (long)B * T;
   Bump b(base);
   w.xs = b.take<float>(M * D);
   w.cs = b.take<float>(M * D);
-  w.xq = b.take<bf16>(M * D);
-  w.cb = b.take<bf16>(M * D);
   w.ctok = b.take<bf16>(M * D);
-  w.xn = b.take<bf16>(M * D);
-  w.qkv = b.take<bf16>(M * 3 * D);
-  w.qh = b.take<bf16>(M * D);
-  w.kh = b.take<bf16>(M * D);
-  w.vt = b.take<bf16>((long)B * D * (((H / 2) * (W / 2) + 7) / 8 * 8));
-  w.att = b.take<bf16>(M * D);
-  w.qc = b.take<bf16>(M * D);
-  w.hm = b.take<bf16>(M * Dm);
+  w.cb = b.take<bf16>((long)(d->cfg.copy_blocks > 0 ? d->cfg.copy_blocks : 1) * M * D);
+  for (int i = 0; i < 2; ++i) {
+    ChainWs& c = w.ch[i];
+    c.xq = b.take<bf16>(M * D);
+    c.xn = b.take<bf16>(M * D);
+    c.qh = b.take<bf16>(M * D);
+    c.kh = b.take<bf16>(M * D);
+    c.vt = b.take<bf16>((long)B * D * ((T + 7) / 8 * 8));
+    c.att = b.take<bf16>(M * D);
+    c.qc = b.take<bf16>(M * D);
+    c.hm = b.take<bf16>(M * Dm);
+  }
   w.sin = b.take<float>((long)B * 4 * 256);
   w.hid = b.take<float>((long)B * 4 * D);
   w.t = b.take<float>((long)B * D);
@@ -266,6 +291,8 @@ struct Ctx {
   Dit* d;
   DitWs w;
   int B, T, M, sumL;
+  int max_len;     // host copy of max_b kv_len[b]
+  long kv_total;   // host copy of sum_b kv_len[b]
   const int *kv_off, *kv_len;
   cudaStream_t s;
 };
@@ -281,89 +308,87 @@ __global__ void cond_scalars_kernel(const float* __restrict__ t, const float* __
   out[3 * B + b] = ar[b];
 }
 
-// one PixArtMSBlock (PixArtMS.py:71-79) on the fp32 stream xs; bf16_copy (optional) receives bf16(xs) at the end
-static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy) {
+// one PixArtMSBlock (PixArtMS.py:71-79) on the fp32 stream xs with the scratch of chain `w`, enqueued on stream `s`;
+// bf16_copy (optional) receives bf16(xs) at the end
+static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs& w, cudaStream_t s) {
   Dit* d = c.d;
-  const BlockW& w = d->blocks[blk];
+  const BlockW& bw = d->blocks[blk];
   const int D = d->cfg.hidden, Dm = D * d->cfg.mlp_ratio, M = c.M, T = c.T;
   const float* mod = c.w.mod + (long)blk * c.B * 6 * D;  // [B][6][D]: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
   const float attn_scale = 1.0f / sqrtf((float)(D / d->cfg.heads));
 
   // x = x + gate_msa * attn(modulate(norm1(x)))
-  IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 0 * D, mod + 1 * D, 6 * D, M, T, D, c.s));
-  static const bool legacy_attn = [] {
-    const char* e = debug_env("IR_ATTN_LEGACY");  // debugging aid: A/B against the mma.sync kernel
-    return e && e[0] == '1';
-  }();
-  if (!legacy_attn) {
+  IR_TRY(ln_modulate_launch(xs, w.xn, mod + 0 * D, mod + 1 * D, 6 * D, M, T, D, s));
+  {
     const int H = d->cfg.heads, hd = D / H, Tp = (T + 7) / 8 * 8;
     GemmArgs g;
-    g.A = c.w.xn; g.lda = D; g.W = w.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
-    g.epi = EPI_QKV; g.bias = w.b_qkv;
-    g.q_heads = c.w.qh; g.k_heads = c.w.kh; g.vt_heads = c.w.vt;
+    g.A = w.xn; g.lda = D; g.W = bw.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+    g.epi = EPI_QKV; g.bias = bw.b_qkv;
+    g.q_heads = w.qh; g.k_heads = w.kh; g.vt_heads = w.vt;
     g.qkv_T = T; g.qkv_Tp = Tp; g.qkv_H = H; g.qkv_hd = hd;
-    IR_TRY(gemm_launch(g, c.s));
+    IR_TRY(gemm_launch(g, s));
     AttnTcArgs a;
-    a.q = c.w.qh; a.k = c.w.kh; a.vt = c.w.vt; a.out = c.w.att; a.ldo = D;
+    a.q = w.qh; a.k = w.kh; a.vt = w.vt; a.out = w.att; a.ldo = D;
     a.B = c.B; a.H = H; a.head_dim = hd; a.T = T; a.Tp = Tp; a.scale = attn_scale;
-    IR_TRY(attention_tc_launch(a, c.s));
-  } else {
-    GemmArgs g;
-    g.A = c.w.xn; g.lda = D; g.W = w.qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
-    g.epi = EPI_BF16; g.bias = w.b_qkv; g.out_bf16 = c.w.qkv; g.ldo_b = 3 * D;
-    IR_TRY(gemm_launch(g, c.s));
-    AttnArgs a;
-    a.q = c.w.qkv; a.k = c.w.qkv + D; a.v = c.w.qkv + 2 * D; a.out = c.w.att;
-    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
-    a.B = c.B; a.heads = d->cfg.heads; a.head_dim = D / d->cfg.heads; a.Tq = T; a.Tk = T; a.scale = attn_scale;
-    IR_TRY(attention_launch(a, c.s));
+    IR_TRY(attention_tc_launch(a, s));
   }
   {
     GemmArgs g;
-    g.A = c.w.att; g.lda = D; g.W = w.proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
-    g.epi = EPI_F32; g.bias = w.b_proj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    g.A = w.att; g.lda = D; g.W = bw.proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_F32; g.bias = bw.b_proj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
     g.gate = mod + 2 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
-    g.out_bf16 = c.w.xq; g.ldo_b = D;  // bf16(x) feeds the cross-attention query projection
-    IR_TRY(gemm_launch(g, c.s));
+    g.out_bf16 = w.xq; g.ldo_b = D;  // bf16(x) feeds the cross-attention query projection
+    IR_TRY(gemm_launch(g, s));
   }
   // x = x + cross_attn(x, y, mask)
   {
     GemmArgs g;
-    g.A = c.w.xq; g.lda = D; g.W = w.q_lin; g.ldw = D; g.M = M; g.N = D; g.K = D;
-    g.epi = EPI_BF16; g.bias = w.b_q; g.out_bf16 = c.w.qc; g.ldo_b = D;
-    IR_TRY(gemm_launch(g, c.s));
+    g.A = w.xq; g.lda = D; g.W = bw.q_lin; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_BF16; g.bias = bw.b_q; g.out_bf16 = w.qc; g.ldo_b = D;
+    IR_TRY(gemm_launch(g, s));
   }
   {
     const bf16* kv = d->ykv + (long)blk * c.sumL * 2 * D;
-    AttnArgs a;
-    a.q = c.w.qc; a.k = kv; a.v = kv + D; a.out = c.w.att;
-    a.ldq = D; a.ldk = a.ldv = 2 * D; a.ldo = D;
-    a.B = c.B; a.heads = d->cfg.heads; a.head_dim = D / d->cfg.heads; a.Tq = T; a.Tk = 0;
-    a.kv_off = c.kv_off; a.kv_len = c.kv_len; a.scale = attn_scale;
-    IR_TRY(attention_launch(a, c.s));
+    XAttnTcArgs a;
+    a.q = w.qc; a.kv = kv; a.out = w.att;
+    a.vt = d->ykv_t + (long)blk * xattention_vt_elems(d->cfg.heads, c.sumL);
+    a.ldq = D; a.ldkv = 2 * D; a.ldo = D;
+    a.B = c.B; a.H = d->cfg.heads; a.head_dim = D / d->cfg.heads; a.T = T; a.sumL = c.sumL;
+    a.kv_off = c.kv_off; a.kv_len = c.kv_len; a.max_len = c.max_len; a.kv_total = c.kv_total; a.scale = attn_scale;
+    IR_TRY(xattention_tc_launch(a, s));
   }
   {
     GemmArgs g;
-    g.A = c.w.att; g.lda = D; g.W = w.cproj; g.ldw = D; g.M = M; g.N = D; g.K = D;
-    g.epi = EPI_F32; g.bias = w.b_cproj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
-    IR_TRY(gemm_launch(g, c.s));
+    g.A = w.att; g.lda = D; g.W = bw.cproj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.epi = EPI_F32; g.bias = bw.b_cproj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    IR_TRY(gemm_launch(g, s));
   }
   // x = x + gate_mlp * mlp(modulate(norm2(x)))
-  IR_TRY(ln_modulate_launch(xs, c.w.xn, mod + 3 * D, mod + 4 * D, 6 * D, M, T, D, c.s));
+  IR_TRY(ln_modulate_launch(xs, w.xn, mod + 3 * D, mod + 4 * D, 6 * D, M, T, D, s));
   {
     GemmArgs g;
-    g.A = c.w.xn; g.lda = D; g.W = w.fc1; g.ldw = D; g.M = M; g.N = Dm; g.K = D;
-    g.epi = EPI_BF16_GELU; g.bias = w.b_fc1; g.out_bf16 = c.w.hm; g.ldo_b = Dm;
-    IR_TRY(gemm_launch(g, c.s));
+    g.A = w.xn; g.lda = D; g.W = bw.fc1; g.ldw = D; g.M = M; g.N = Dm; g.K = D;
+    g.epi = EPI_BF16_GELU; g.bias = bw.b_fc1; g.out_bf16 = w.hm; g.ldo_b = Dm;
+    IR_TRY(gemm_launch(g, s));
   }
   {
     GemmArgs g;
-    g.A = c.w.hm; g.lda = Dm; g.W = w.fc2; g.ldw = Dm; g.M = M; g.N = D; g.K = Dm;
-    g.epi = EPI_F32; g.bias = w.b_fc2; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    g.A = w.hm; g.lda = Dm; g.W = bw.fc2; g.ldw = Dm; g.M = M; g.N = D; g.K = Dm;
+    g.epi = EPI_F32; g.bias = bw.b_fc2; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
     g.gate = mod + 5 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
     g.out_bf16 = bf16_copy; g.ldo_b = D;
-    IR_TRY(gemm_launch(g, c.s));
+    IR_TRY(gemm_launch(g, s));
   }
+  return IR_OK;
+}
+
+// second stream + events of the dual-chain schedule, created on first use (one set per handle)
+static int ensure_side_stream(Dit* d) {
+  if (d->side) return IR_OK;
+  IR_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
+  IR_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  d->ev_c.resize(d->cfg.copy_blocks);
+  for (auto& e : d->ev_c) IR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return IR_OK;
 }
 
@@ -398,6 +423,11 @@ static int ensure_ykv(Dit* d, int sumL) {
   d->ykv_sumL = -1;
   IR_CUDA_CHECK(cudaMalloc(&d->ykv, (size_t)need_kv * sizeof(bf16)));
   d->ykv_cap = need_kv;
+  const long need_t = (long)d->nblk * xattention_vt_elems(d->cfg.heads, sumL) + 64;   // sumL <= capacity sumL: always fits
+  if (d->ykv_t) IR_CUDA_CHECK(cudaFree(d->ykv_t));
+  d->ykv_t = nullptr;
+  IR_CUDA_CHECK(cudaMalloc(&d->ykv_t, (size_t)need_t * sizeof(bf16)));
+  d->ykv_t_cap = need_t;
   return IR_OK;
 }
 
@@ -427,6 +457,8 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   IR_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.H % 2 == 0 && a.W % 2 == 0, "dit_forward: bad latent shape %dx%dx%d",
              a.B, a.H, a.W);
   IR_REQUIRE(a.sumL > 0 && a.kv_off && a.kv_len, "dit_forward: caption token table missing");
+  IR_REQUIRE(a.max_len > 0 && a.max_len <= a.sumL + 7 && a.max_len <= 384,
+             "dit_forward: caption key window %d out of range (1..min(sum_l + 7, 384))", a.max_len);
   IR_REQUIRE(!a.c || d->cfg.copy_blocks > 0, "dit_forward: control input given but the model has no control blocks");
   for (const ParamEntry& e : d->params)
     IR_REQUIRE(e.loaded, "dit_forward: parameter '%s' was never loaded", e.name.c_str());
@@ -447,6 +479,8 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   c.sumL = a.sumL;
   c.kv_off = a.kv_off;
   c.kv_len = a.kv_len;
+  c.max_len = a.max_len;
+  c.kv_total = a.kv_total;
   carve(d, c.w, a.workspace, a.B, a.H, a.W, a.sumL);
   const int D = d->cfg.hidden, B = a.B;
 
@@ -497,6 +531,7 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
     g3.epi = EPI_BF16; g3.bias = d->b_kv_all; g3.stride_bias = 2 * D;
     g3.out_bf16 = d->ykv; g3.ldo_b = 2 * D; g3.stride_ob = (long)a.sumL * 2 * D;
     IR_TRY(gemm_launch(g3, s));
+    IR_TRY(xattention_transpose_v(d->ykv, d->ykv_t, d->nblk, d->cfg.heads, a.sumL, 2 * D, s));
     d->ykv_sumL = a.sumL;
   }
 
@@ -504,27 +539,49 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   IR_TRY(patch_embed_launch(a.x, d->xw_t, d->xb, d->pos, c.w.xs, nullptr, B, d->cfg.in_ch, a.H, a.W, D, s));
   if (a.c) IR_TRY(patch_embed_launch(a.c, d->xw_t, d->xb, d->pos, nullptr, c.w.ctok, B, d->cfg.in_ch, a.H, a.W, D, s));
 
-  // ---- blocks (pixart_controlnet.py:234-247)
-  IR_TRY(run_block(c, 0, c.w.xs, nullptr));
+  // ---- blocks (pixart_controlnet.py:234-247). Dependencies: c_1 = copied[0](x_0 + before_proj(c)), c_{j+1} = copied[j](c_j),
+  // x_i = base[i](x_{i-1} + after_proj_i(c_i)): the whole control chain depends on the base chain only through x_0, so it runs
+  // on a second stream, ahead of the base chain, which waits for c_i (one event per control block) before its i-th
+  // injection. Two independent kernels are then always queued: one chain's launch gaps, prologues, epilogue tails and
+  // partial last waves (256 attention CTAs on 148 SMs) are filled by the other chain's CTAs. Same kernels, same
+  // per-kernel arithmetic: bit-identical to the single-stream order. The profile pass (per-kernel CUDA-event timing) keeps
+  // the single-stream order so that a kernel's duration is its own.
+  IR_TRY(run_block(c, 0, c.w.xs, nullptr, c.w.ch[0], s));
   int next = 1;
   if (a.c) {
+    const int ncb = d->cfg.copy_blocks;
+    const bool dual = dual_chain_enabled() && !prof_enabled() && ncb > 0;
+    cudaStream_t cs_stream = s;
+    if (dual) {
+      IR_TRY(ensure_side_stream(d));
+      cs_stream = d->side;
+      IR_CUDA_CHECK(cudaEventRecord(d->ev_fork, s));
+      IR_CUDA_CHECK(cudaStreamWaitEvent(cs_stream, d->ev_fork, 0));
+    }
+    const ChainWs& cw = c.w.ch[dual ? 1 : 0];
     // controlnet[0]: c = before_proj(c); c = copied_block(x + c)
     GemmArgs g;
     g.A = c.w.ctok; g.lda = D; g.W = d->before_proj; g.ldw = D; g.M = c.M; g.N = D; g.K = D;
     g.epi = EPI_F32; g.bias = d->b_before; g.out_f32 = c.w.cs; g.resid_f32 = c.w.xs; g.ldo_f = D;
-    IR_TRY(gemm_launch(g, s));
-    for (int i = 1; i <= d->cfg.copy_blocks; ++i) {
-      IR_TRY(run_block(c, d->cfg.depth + i - 1, c.w.cs, c.w.cb));
+    IR_TRY(gemm_launch(g, cs_stream));
+    for (int i = 1; i <= ncb; ++i) {
+      bf16* cb_i = c.w.cb + (long)(i - 1) * c.M * D;
+      IR_TRY(run_block(c, d->cfg.depth + i - 1, c.w.cs, cb_i, cw, cs_stream));
+      if (dual) {
+        IR_CUDA_CHECK(cudaEventRecord(d->ev_c[i - 1], cs_stream));
+        IR_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_c[i - 1], 0));
+      }
       // x = x + after_proj(c)
       GemmArgs ga;
-      ga.A = c.w.cb; ga.lda = D; ga.W = d->after_proj[i - 1]; ga.ldw = D; ga.M = c.M; ga.N = D; ga.K = D;
+      ga.A = cb_i; ga.lda = D; ga.W = d->after_proj[i - 1]; ga.ldw = D; ga.M = c.M; ga.N = D; ga.K = D;
       ga.epi = EPI_F32; ga.bias = d->b_after[i - 1]; ga.out_f32 = c.w.xs; ga.resid_f32 = c.w.xs; ga.ldo_f = D;
       IR_TRY(gemm_launch(ga, s));
-      IR_TRY(run_block(c, i, c.w.xs, nullptr));
+      IR_TRY(run_block(c, i, c.w.xs, nullptr, c.w.ch[0], s));
     }
-    next = d->cfg.copy_blocks + 1;
+    // the base chain has waited for the last control event: the side stream is joined
+    next = ncb + 1;
   }
-  for (int i = next; i < d->cfg.depth; ++i) IR_TRY(run_block(c, i, c.w.xs, nullptr));
+  for (int i = next; i < d->cfg.depth; ++i) IR_TRY(run_block(c, i, c.w.xs, nullptr, c.w.ch[0], s));
 
   // ---- final layer + unpatchify
   IR_TRY(final_layer_launch(c.w.xs, d->fin_table, c.w.t, d->fin_w, d->fin_b, a.out, B, gh, gw, D, d->cfg.out_ch, s));

@@ -70,8 +70,13 @@ struct Dit {
   float* pos = nullptr;  // (gh*gw, D) table for the last (gh, gw); grow-only buffer
   long pos_cap = 0;      // capacity in elements
   int pos_gh = 0, pos_gw = 0;
+  cudaStream_t side = nullptr;       // control-chain stream of the dual-chain schedule (created on first use)
+  cudaEvent_t ev_fork = nullptr;     // base block 0 done -> the control chain may start
+  std::vector<cudaEvent_t> ev_c;     // [copy_blocks] control block i done -> the base chain may inject c_i
   bf16* ykv = nullptr;   // [nblk][sumL][2D] caption K/V of the last caption
   long ykv_cap = 0;      // capacity in elements
+  bf16* ykv_t = nullptr; // [nblk][H][72][roundup8(sumL)] V halves transposed (keys contiguous) for the cross-attention TMA
+  long ykv_t_cap = 0;
   int ykv_sumL = -1;
 };
 
@@ -92,6 +97,8 @@ struct DitForwardArgs {
   const float* aspect = nullptr;    // device (B)
   float* out = nullptr;             // (B, out_ch, H, W)
   int B = 0, H = 0, W = 0, sumL = 0;
+  int max_len = 0;                  // host copy of max_b (kv_off[b] % 8 + kv_len[b]) (<= 384): the cross-attention key window
+  long kv_total = 0;                // host copy of sum_b kv_len[b] (FLOP accounting only)
   int reuse_caption = 0;            // 1: caption K/V of the previous call are still valid
   void* workspace = nullptr;
   size_t workspace_bytes = 0;

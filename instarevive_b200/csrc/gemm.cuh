@@ -75,7 +75,7 @@ struct GemmArgs {
 };
 
 // bf16 tiled tensor map (innermost dimension first; strides in bytes for dims 1..rank-1; zero OOB fill).
-// swizzle_bytes: 128 or 32 (the inner box extent must equal it).
+// swizzle_bytes: 128 or 32 (the inner box extent must equal it), or 0 = no swizzle (inner box extent a multiple of 16 B).
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int swizzle_bytes);
 int device_num_sms();

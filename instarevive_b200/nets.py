@@ -313,8 +313,12 @@ class ControlPixArtMSHalf(nn.Module):
         else:
             raise ValueError(f"caption batch {ny} does not match latent batch {bs}")
         dev = y.device
+        if max(lens) > 384:
+            raise ValueError(f"captions of more than 384 valid tokens are not supported (got {max(lens)})")
         tens = (torch.cat(rows).to(torch.int32).to(dev), torch.tensor(kv_off, dtype=torch.int32, device=dev),
-                torch.tensor(kv_len, dtype=torch.int32, device=dev), int(sum(lens)))
+                torch.tensor(kv_len, dtype=torch.int32, device=dev), int(sum(lens)),
+                # key-window size of the cross-attention kernel: its TMA window starts at the packed row rounded down to 8
+                int(max((o % 8) + l for o, l in zip(kv_off, kv_len))), int(sum(kv_len)))
         self._cap_key, self._cap_tensors = key, tens
         return tens + (False,)
 
@@ -357,14 +361,14 @@ class ControlPixArtMSHalf(nn.Module):
         hw, ar = hw.contiguous(), ar.contiguous()
         if y.dim() != 4 or y.shape[1] != 1 or y.shape[3] != self.caption_channels:
             raise ValueError(f"y must be (N,1,L,{self.caption_channels}), got {tuple(y.shape)}")
-        y_index, kv_off, kv_len, sum_l, reuse = self._caption_tables(y, mask, bs)
+        y_index, kv_off, kv_len, sum_l, max_l, kv_total, reuse = self._caption_tables(y, mask, bs)
         out = torch.empty(bs, self.out_channels, H, W, **f32)
         with torch.cuda.device(dev):
             need = L.ir_dit_workspace_bytes(self._handle, bs, H, W, sum_l)
             ws = self._workspace(need, dev)
             _lib.check(L.ir_dit_forward(self._handle, xx.data_ptr(), _lib.ptr(cc), ts.data_ptr(), yy.data_ptr(),
                                         y_index.data_ptr(), kv_off.data_ptr(), kv_len.data_ptr(), hw.data_ptr(),
-                                        ar.data_ptr(), out.data_ptr(), bs, H, W, sum_l, int(reuse), ws.data_ptr(),
+                                        ar.data_ptr(), out.data_ptr(), bs, H, W, sum_l, max_l, kv_total, int(reuse), ws.data_ptr(),
                                         ws.numel(), _lib.stream_ptr()), "ir_dit_forward")
         return out
 

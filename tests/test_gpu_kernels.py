@@ -209,6 +209,7 @@ def test_varlen_cross_attention(ctx, B, T, lens):
     kv = torch.randn(sum(lens), 2 * D, generator=g).to(dev).bfloat16()
     off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=dev)
     ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    win = max((sum(lens[:i]) % 8) + lens[i] for i in range(B))   # key window: the TMA box starts at a multiple of 8 rows
     out = torch.empty(B * T, D, device=dev, dtype=torch.bfloat16)
     _lib.check(L.ir_attention_bf16(qm.data_ptr(), kv.data_ptr(), kv.data_ptr() + 2 * D, out.data_ptr(), D, 2 * D, 2 * D, D,
                                    B, heads, hd, T, 0, off.data_ptr(), ln.data_ptr(), hd ** -0.5, _lib.stream_ptr()))
@@ -220,6 +221,42 @@ def test_varlen_cross_attention(ctx, B, T, lens):
         refs.append(F.scaled_dot_product_attention(q, kk[:, 0].permute(1, 0, 2), kk[:, 1].permute(1, 0, 2))
                     .permute(1, 0, 2).reshape(T, D))
     _close(out, torch.cat(refs), 1e-2)
+
+
+@pytest.mark.parametrize("B,T,lens", [(2, 1024, [120, 77]), (3, 600, [1, 300, 64]), (1, 100, [33]), (1, 4096, [77]),
+                                      (4, 4000, [120, 300, 77, 5]), (2, 256, [128, 16]), (1, 512, [384]), (25, 1024, [77] * 25),
+                                      (3, 1024, [256, 257, 129])])
+def test_cross_attention_tcgen05(ctx, B, T, lens):
+    """The DiT path's cross-attention kernel (xattention_tc.cu: tcgen05 TS-form MMAs, S / P / O / Q in TMEM, K by TMA, V
+    transposed in shared memory) vs fp32 SDPA per (sample, head) on ragged caption lengths: 1 token, exactly one key tile
+    (128), two TMA boxes (> 256 keys), the 384-token maximum, partial query tiles, 1 and 2 CTAs per SM."""
+    _lib, L, dev = ctx
+    heads, hd = 16, 72
+    D = heads * hd
+    g = torch.Generator().manual_seed(B * 7 + T)
+    qm = torch.randn(B * T, D, generator=g).to(dev).bfloat16()
+    kv = torch.randn(sum(lens), 2 * D, generator=g).to(dev).bfloat16()
+    off = torch.tensor([sum(lens[:i]) for i in range(B)], dtype=torch.int32, device=dev)
+    ln = torch.tensor(lens, dtype=torch.int32, device=dev)
+    win = max((sum(lens[:i]) % 8) + lens[i] for i in range(B))   # key window: the TMA box starts at a multiple of 8 rows
+    out = torch.full((B * T, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    vt = torch.empty(L.ir_cross_attention_vt_bytes(heads, sum(lens)), dtype=torch.uint8, device=dev)
+    _lib.check(L.ir_cross_attention_tc_bf16(qm.data_ptr(), kv.data_ptr(), vt.data_ptr(), out.data_ptr(), D, 2 * D, D, B, heads, hd, T,
+                                            sum(lens), off.data_ptr(), ln.data_ptr(), win, hd ** -0.5, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    refs = []
+    for b in range(B):
+        q = qm[b * T:(b + 1) * T].float().view(T, heads, hd).permute(1, 0, 2)
+        kk = kv[int(off[b]):int(off[b]) + lens[b]].float().view(-1, 2, heads, hd)
+        refs.append(F.scaled_dot_product_attention(q, kk[:, 0].permute(1, 0, 2), kk[:, 1].permute(1, 0, 2))
+                    .permute(1, 0, 2).reshape(T, D))
+    _close(out, torch.cat(refs), 1e-2)
+    # a shared caption (tiles of one image: every sample reads the same rows) and a second launch are bit-reproducible
+    out2 = torch.empty_like(out)
+    _lib.check(L.ir_cross_attention_tc_bf16(qm.data_ptr(), kv.data_ptr(), vt.data_ptr(), out2.data_ptr(), D, 2 * D, D, B, heads, hd, T,
+                                            sum(lens), off.data_ptr(), ln.data_ptr(), win, hd ** -0.5, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
 
 
 def test_ln_modulate(ctx):
