@@ -88,6 +88,10 @@ size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l);
  * caption K/V of all blocks (PixArt_blocks.py:47-50; up to max_sum_l packed caption tokens) -- so that no forward calls
  * cudaMalloc. Optional: forwards grow the buffers on demand (grow-only, never freed before ir_dit_destroy). */
 int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l);
+/* CUDA-graph replay of ir_dit_forward (default on): the second call with a given (B, H, W, caption layout, workspace)
+ * captures the forward, later calls replay it (inputs / output are staged through fixed buffers of the workspace).
+ * enable = 0 switches back to plain stream-ordered launches and drops the cached graphs. */
+int ir_dit_set_graphs(ir_dit* h, int enable);
 /*
  * x, c: (B,4,H,W) fp32 latents (c may be NULL: plain 28-block path); timestep: (B) fp32;
  * y: (rows,4096) fp32 caption embeddings; y_index: device int32 (sum_l) valid rows of y, sample-major;

@@ -27,6 +27,7 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = debug_env("IR_NO_PDL");
@@ -214,6 +215,15 @@ int ir_dit_load_param(ir_dit* h, const char* name, const float* src_dev, long lo
 
 size_t ir_dit_workspace_bytes(const ir_dit* h, int B, int H, int W, int sum_l) {
   return h ? dit_workspace_bytes(h->d, B, H, W, sum_l) : 0;
+}
+
+int ir_dit_set_graphs(ir_dit* h, int enable) {
+  if (!h) {
+    set_last_error("ir_dit_set_graphs: null handle");
+    return IR_ERR_INVALID;
+  }
+  dit_set_graphs(h->d, enable != 0);
+  return IR_OK;
 }
 
 int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l) {

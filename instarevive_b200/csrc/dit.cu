@@ -174,8 +174,12 @@ static bool dual_chain_enabled() {
   return on;
 }
 
+static void destroy_graphs(Dit* d);
+
 void dit_destroy(Dit* d) {
   if (!d) return;
+  destroy_graphs(d);
+  if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
   if (d->side) {
     cudaStreamSynchronize(d->side);
     cudaStreamDestroy(d->side);
@@ -247,6 +251,9 @@ struct DitWs {
   bf16* ctok;                     // patch-embedded control tokens (bf16, before_proj input)
   float *sin, *hid, *t, *t0, *mod;
   bf16 *yg, *yh, *ye;
+  // fixed-address staging of the per-call inputs / output for CUDA-graph replay (the caller's tensors move between calls)
+  float *g_x, *g_c, *g_ts, *g_hw, *g_ar, *g_out;
+  int *g_kvoff, *g_kvlen;
 };
 
 static size_t carve(const Dit* d, DitWs& w, void* base, int B, int H, int W, int sumL) {
@@ -278,6 +285,15 @@ static size_t carve(const Dit* d, DitWs& w, void* base, int B, int H, int W, int
   w.yg = b.take<bf16>(L * d->cfg.caption_ch);
   w.yh = b.take<bf16>(L * D);
   w.ye = b.take<bf16>(L * D);
+  const long px = (long)B * H * W;
+  w.g_x = b.take<float>(px * d->cfg.in_ch);
+  w.g_c = b.take<float>(px * d->cfg.in_ch);
+  w.g_out = b.take<float>(px * d->cfg.out_ch);
+  w.g_ts = b.take<float>(B);
+  w.g_hw = b.take<float>(2L * B);
+  w.g_ar = b.take<float>(B);
+  w.g_kvoff = b.take<int>(B);
+  w.g_kvlen = b.take<int>(B);
   return (b.off + 255) & ~size_t(255);
 }
 
@@ -452,23 +468,9 @@ int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, 
   return patch_embed_launch(x, d->xw_t, d->xb, d->pos, tokens, nullptr, B, d->cfg.in_ch, H, W, d->cfg.hidden, s);
 }
 
-int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
-  IR_REQUIRE(a.x && a.timestep && a.out && a.img_hw && a.aspect, "dit_forward: null input");
-  IR_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.H % 2 == 0 && a.W % 2 == 0, "dit_forward: bad latent shape %dx%dx%d",
-             a.B, a.H, a.W);
-  IR_REQUIRE(a.sumL > 0 && a.kv_off && a.kv_len, "dit_forward: caption token table missing");
-  IR_REQUIRE(a.max_len > 0 && a.max_len <= a.sumL + 7 && a.max_len <= 384,
-             "dit_forward: caption key window %d out of range (1..min(sum_l + 7, 384))", a.max_len);
-  IR_REQUIRE(!a.c || d->cfg.copy_blocks > 0, "dit_forward: control input given but the model has no control blocks");
-  for (const ParamEntry& e : d->params)
-    IR_REQUIRE(e.loaded, "dit_forward: parameter '%s' was never loaded", e.name.c_str());
-  const size_t need = dit_workspace_bytes(d, a.B, a.H, a.W, a.sumL);
-  if (!a.workspace || a.workspace_bytes < need) {
-    set_last_error("dit_forward: workspace too small (%zu < %zu bytes)", a.workspace_bytes, need);
-    return IR_ERR_WORKSPACE;
-  }
-  IR_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0, "dit_forward: workspace must be 256-byte aligned");
-
+// everything after the caption branch: conditioning, patch embedding, the 28 (+13) blocks, final layer. Reads a.x / a.c /
+// a.timestep / a.img_hw / a.aspect / a.kv_off / a.kv_len, writes a.out; this is the part a CUDA graph replays.
+static int dit_forward_body(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   Ctx c;
   c.d = d;
   c.s = s;
@@ -508,31 +510,6 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
     IR_TRY(small_linear_launch(h_ar, Dz, d->ar_w2, d->ar_b2, c.w.t + 2 * Dz, Dz, 1, D, B, Dz, Dz, ACT_NONE, ACT_NONE, 1, s));
     IR_TRY(small_linear_launch(c.w.t, D, d->tb_w, d->tb_b, c.w.t0, 6 * D, 1, 6 * D, B, 6 * D, D, ACT_SILU, ACT_NONE, 0, s));
     IR_TRY(adaln_table_launch(d->tables, c.w.t0, c.w.mod, d->nblk, B, D, s));
-  }
-
-  // ---- caption: y_embedder on the valid tokens, then K/V projections of all blocks in one batched GEMM
-  if (!a.reuse_caption || d->ykv_sumL != a.sumL) {
-    IR_REQUIRE(a.y && a.y_index, "dit_forward: caption embeddings missing");
-    IR_TRY(ensure_ykv(d, a.sumL));
-    IR_TRY(gather_rows_launch(a.y, a.y_index, c.w.yg, a.sumL, d->cfg.caption_ch, s));
-    GemmArgs g1;
-    g1.A = c.w.yg; g1.lda = d->cfg.caption_ch; g1.W = d->y_fc1; g1.ldw = d->cfg.caption_ch;
-    g1.M = a.sumL; g1.N = D; g1.K = d->cfg.caption_ch;
-    g1.epi = EPI_BF16_GELU; g1.bias = d->y_b1; g1.out_bf16 = c.w.yh; g1.ldo_b = D;
-    IR_TRY(gemm_launch(g1, s));
-    GemmArgs g2;
-    g2.A = c.w.yh; g2.lda = D; g2.W = d->y_fc2; g2.ldw = D; g2.M = a.sumL; g2.N = D; g2.K = D;
-    g2.epi = EPI_BF16; g2.bias = d->y_b2; g2.out_bf16 = c.w.ye; g2.ldo_b = D;
-    IR_TRY(gemm_launch(g2, s));
-    GemmArgs g3;
-    g3.A = c.w.ye; g3.lda = D; g3.strideA = 0;
-    g3.W = d->kv_all; g3.ldw = D; g3.strideW = (long)2 * D * D;
-    g3.M = a.sumL; g3.N = 2 * D; g3.K = D; g3.batch = d->nblk;
-    g3.epi = EPI_BF16; g3.bias = d->b_kv_all; g3.stride_bias = 2 * D;
-    g3.out_bf16 = d->ykv; g3.ldo_b = 2 * D; g3.stride_ob = (long)a.sumL * 2 * D;
-    IR_TRY(gemm_launch(g3, s));
-    IR_TRY(xattention_transpose_v(d->ykv, d->ykv_t, d->nblk, d->cfg.heads, a.sumL, 2 * D, s));
-    d->ykv_sumL = a.sumL;
   }
 
   // ---- tokens
@@ -586,6 +563,156 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   // ---- final layer + unpatchify
   IR_TRY(final_layer_launch(c.w.xs, d->fin_table, c.w.t, d->fin_w, d->fin_b, a.out, B, gh, gw, D, d->cfg.out_ch, s));
   return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA-graph replay
+// The forward is ~450 launches whose sizes, order and device pointers are fixed for a given (batch, latent size, caption
+// layout, workspace): the second call with a key captures the body (both chains: the fork / join events are captured with
+// it) into a graph, later calls copy the inputs to fixed staging buffers, launch the graph and copy the output back. The
+// caption branch (y_embedder + K/V of all blocks; runs when the caption changes) stays outside the graph.
+static void destroy_graphs(Dit* d) {
+  for (DitGraph& g : d->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  }
+  d->graphs.clear();
+}
+
+static bool stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
+  IR_REQUIRE(a.x && a.timestep && a.out && a.img_hw && a.aspect, "dit_forward: null input");
+  IR_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.H % 2 == 0 && a.W % 2 == 0, "dit_forward: bad latent shape %dx%dx%d",
+             a.B, a.H, a.W);
+  IR_REQUIRE(a.sumL > 0 && a.kv_off && a.kv_len, "dit_forward: caption token table missing");
+  IR_REQUIRE(a.max_len > 0 && a.max_len <= a.sumL + 7 && a.max_len <= 384,
+             "dit_forward: caption key window %d out of range (1..min(sum_l + 7, 384))", a.max_len);
+  IR_REQUIRE(!a.c || d->cfg.copy_blocks > 0, "dit_forward: control input given but the model has no control blocks");
+  for (const ParamEntry& e : d->params)
+    IR_REQUIRE(e.loaded, "dit_forward: parameter '%s' was never loaded", e.name.c_str());
+  const size_t need = dit_workspace_bytes(d, a.B, a.H, a.W, a.sumL);
+  if (!a.workspace || a.workspace_bytes < need) {
+    set_last_error("dit_forward: workspace too small (%zu < %zu bytes)", a.workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  IR_REQUIRE((reinterpret_cast<uintptr_t>(a.workspace) & 255) == 0, "dit_forward: workspace must be 256-byte aligned");
+
+  DitWs w;
+  carve(d, w, a.workspace, a.B, a.H, a.W, a.sumL);
+  const int D = d->cfg.hidden;
+  IR_TRY(ensure_pos(d, a.H / 2, a.W / 2, s));
+  // ---- caption: y_embedder on the valid tokens, then K/V projections of all blocks in one batched GEMM
+  if (!a.reuse_caption || d->ykv_sumL != a.sumL) {
+    IR_REQUIRE(a.y && a.y_index, "dit_forward: caption embeddings missing");
+    IR_TRY(ensure_ykv(d, a.sumL));
+    IR_TRY(gather_rows_launch(a.y, a.y_index, w.yg, a.sumL, d->cfg.caption_ch, s));
+    GemmArgs g1;
+    g1.A = w.yg; g1.lda = d->cfg.caption_ch; g1.W = d->y_fc1; g1.ldw = d->cfg.caption_ch;
+    g1.M = a.sumL; g1.N = D; g1.K = d->cfg.caption_ch;
+    g1.epi = EPI_BF16_GELU; g1.bias = d->y_b1; g1.out_bf16 = w.yh; g1.ldo_b = D;
+    IR_TRY(gemm_launch(g1, s));
+    GemmArgs g2;
+    g2.A = w.yh; g2.lda = D; g2.W = d->y_fc2; g2.ldw = D; g2.M = a.sumL; g2.N = D; g2.K = D;
+    g2.epi = EPI_BF16; g2.bias = d->y_b2; g2.out_bf16 = w.ye; g2.ldo_b = D;
+    IR_TRY(gemm_launch(g2, s));
+    GemmArgs g3;
+    g3.A = w.ye; g3.lda = D; g3.strideA = 0;
+    g3.W = d->kv_all; g3.ldw = D; g3.strideW = (long)2 * D * D;
+    g3.M = a.sumL; g3.N = 2 * D; g3.K = D; g3.batch = d->nblk;
+    g3.epi = EPI_BF16; g3.bias = d->b_kv_all; g3.stride_bias = 2 * D;
+    g3.out_bf16 = d->ykv; g3.ldo_b = 2 * D; g3.stride_ob = (long)a.sumL * 2 * D;
+    IR_TRY(gemm_launch(g3, s));
+    IR_TRY(xattention_transpose_v(d->ykv, d->ykv_t, d->nblk, d->cfg.heads, a.sumL, 2 * D, s));
+    d->ykv_sumL = a.sumL;
+  }
+
+
+  const bool use_graph = d->graphs_enabled && !prof_enabled() && !stream_is_capturing(s);
+  if (!use_graph) return dit_forward_body(d, a, s);
+
+  DitGraphKey key;
+  key.B = a.B; key.H = a.H; key.W = a.W; key.sumL = a.sumL; key.max_len = a.max_len; key.has_c = a.c ? 1 : 0;
+  key.ws = a.workspace; key.pos = d->pos; key.ykv = d->ykv; key.ykv_t = d->ykv_t;
+  DitGraph* hit = nullptr;
+  for (DitGraph& g : d->graphs)
+    if (g.key == key) hit = &g;
+  if (!hit) {
+    // first call with this key: run eagerly (lazy one-time initialisation -- shared-memory opt-ins, the side stream, the
+    // driver entry point -- happens outside any capture) and remember the key
+    if (!d->graphs.empty() && d->graphs[0].key.ws != a.workspace) destroy_graphs(d);   // the workspace moved: all stale
+    if (d->graphs.size() >= 8) destroy_graphs(d);
+    DitGraph g;
+    g.key = key;
+    d->graphs.push_back(g);
+    return dit_forward_body(d, a, s);
+  }
+  // stage the inputs at fixed addresses
+  const size_t px = (size_t)a.B * a.H * a.W;
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_x, a.x, px * d->cfg.in_ch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (a.c) IR_CUDA_CHECK(cudaMemcpyAsync(w.g_c, a.c, px * d->cfg.in_ch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_ts, a.timestep, a.B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_hw, a.img_hw, 2 * a.B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_ar, a.aspect, a.B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_kvoff, a.kv_off, a.B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  IR_CUDA_CHECK(cudaMemcpyAsync(w.g_kvlen, a.kv_len, a.B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (!hit->exec) {
+    DitForwardArgs ga = a;
+    ga.x = w.g_x;
+    ga.c = a.c ? w.g_c : nullptr;
+    ga.timestep = w.g_ts;
+    ga.img_hw = w.g_hw;
+    ga.aspect = w.g_ar;
+    ga.kv_off = w.g_kvoff;
+    ga.kv_len = w.g_kvlen;
+    ga.out = w.g_out;
+    const long long before = launch_count_value();
+    // capture on a stream of our own: the caller's stream may be the legacy default stream, which cannot be captured;
+    // nothing executes during capture, and the instantiated graph is launched on the caller's stream
+    if (!d->cap_stream) IR_CUDA_CHECK(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+    if (cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      d->graphs_enabled = false;
+      destroy_graphs(d);
+      return dit_forward_body(d, a, s);
+    }
+    const int st = dit_forward_body(d, ga, d->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(d->cap_stream, &graph);
+    if (st != IR_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (st == IR_OK) set_last_error("dit_forward: graph capture failed: %s", cudaGetErrorString(ce));
+      d->graphs_enabled = false;   // do not try again on this handle; the eager path below still serves the call
+      destroy_graphs(d);
+      return st != IR_OK ? st : dit_forward_body(d, a, s);
+    }
+    hit->launches = (int)(launch_count_value() - before);
+    count_launch(-hit->launches);   // nothing ran during capture; replays are counted below
+    const cudaError_t ie = cudaGraphInstantiate(&hit->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      hit->exec = nullptr;
+      cudaGetLastError();
+      d->graphs_enabled = false;
+      destroy_graphs(d);
+      return dit_forward_body(d, a, s);
+    }
+  }
+  IR_CUDA_CHECK(cudaGraphLaunch(hit->exec, s));
+  count_launch(hit->launches);
+  IR_CUDA_CHECK(cudaMemcpyAsync(a.out, w.g_out, px * d->cfg.out_ch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return IR_OK;
+}
+
+void dit_set_graphs(Dit* d, bool on) {
+  d->graphs_enabled = on;
+  if (!on) destroy_graphs(d);
 }
 
 }  // namespace ir

@@ -39,6 +39,20 @@ struct BlockW {
   const float *b_qkv, *b_proj, *b_q, *b_kv, *b_cproj, *b_fc1, *b_fc2;
 };
 
+struct DitGraphKey {
+  int B = 0, H = 0, W = 0, sumL = 0, max_len = 0, has_c = 0;
+  const void *ws = nullptr, *pos = nullptr, *ykv = nullptr, *ykv_t = nullptr;
+  bool operator==(const DitGraphKey& o) const {
+    return B == o.B && H == o.H && W == o.W && sumL == o.sumL && max_len == o.max_len && has_c == o.has_c && ws == o.ws &&
+           pos == o.pos && ykv == o.ykv && ykv_t == o.ykv_t;
+  }
+};
+struct DitGraph {
+  DitGraphKey key;
+  cudaGraphExec_t exec = nullptr;   // null: the key was seen once (eager run), capture on the next call
+  int launches = 0;                 // kernel launches one replay stands for (ir_launch_count accounting)
+};
+
 struct Dit {
   DitConfig cfg;
   int nblk = 0;  // depth + copy_blocks
@@ -73,6 +87,9 @@ struct Dit {
   cudaStream_t side = nullptr;       // control-chain stream of the dual-chain schedule (created on first use)
   cudaEvent_t ev_fork = nullptr;     // base block 0 done -> the control chain may start
   std::vector<cudaEvent_t> ev_c;     // [copy_blocks] control block i done -> the base chain may inject c_i
+  bool graphs_enabled = true;        // replay the forward as a CUDA graph from the third call with a key on
+  std::vector<DitGraph> graphs;
+  cudaStream_t cap_stream = nullptr; // capture happens on this stream (the caller's may be the uncapturable legacy stream)
   bf16* ykv = nullptr;   // [nblk][sumL][2D] caption K/V of the last caption
   long ykv_cap = 0;      // capacity in elements
   bf16* ykv_t = nullptr; // [nblk][H][72][roundup8(sumL)] V halves transposed (keys contiguous) for the cross-attention TMA
@@ -108,6 +125,7 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s);
 // pre-size the handle-owned caches (position table for up to max_tokens tokens, caption K/V for up to max_sum_l packed
 // caption tokens) so that no forward allocates
 int dit_reserve(Dit* d, int max_tokens, int max_sum_l);
+void dit_set_graphs(Dit* d, bool on);
 int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, cudaStream_t s);
 
 }  // namespace ir

@@ -102,6 +102,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 
 // number of kernel launches issued by this library since load (bench.py's gpu_launches counter)
 void count_launch(int n = 1);
+long long launch_count_value();
 
 // Optional per-launch timing (bench.py roofline pass): CUDA events around the launches of one kernel class.
 enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_XATTN = 3, PROF_NUM = 8 };   // ATTN: tcgen05 self-attention; XATTN: var-len cross-attention

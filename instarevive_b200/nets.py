@@ -273,6 +273,12 @@ class ControlPixArtMSHalf(nn.Module):
         self._packed_version = ver
         self._cap_key = None
 
+    def set_cuda_graphs(self, enable: bool) -> None:
+        """CUDA-graph replay of the forward (default on: from the third call with a given batch / latent size / caption
+        layout the ~450 launches are replayed as one graph). Off = plain stream-ordered launches."""
+        self.pack()
+        _lib.check(_lib.lib().ir_dit_set_graphs(self._handle, 1 if enable else 0), "ir_dit_set_graphs")
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None):

@@ -119,6 +119,39 @@ def test_caption_cache_honours_a_new_caption_at_a_recycled_address(small_model):
     assert torch.equal(run(yb), out1)
 
 
+def test_cuda_graph_replay_is_bit_identical_to_eager_launches(small_model):
+    """ir_dit_forward replays the forward as a CUDA graph from the third call with a key (first call eager, second
+    captures). Every variant -- eager, capturing call, replays, replays with NEW input tensors at other addresses, a
+    different shape in between, graphs switched off -- must give bit-identical outputs for identical inputs."""
+    from instarevive_b200 import weights
+    dev = _cuda()
+    x, ts, y, mask, info = weights.make_inputs(2, 32, 48, seed=3, lens=(77, 40))
+    x2 = torch.randn(2, 4, 32, 48, generator=torch.Generator().manual_seed(9))
+    info = {k: v.to(dev) for k, v in info.items()}
+    yd, md, td = y.to(dev), mask.to(dev), ts.to(dev)
+
+    def run(xx):
+        xd = xx.to(dev)   # a fresh device tensor every call: the graph must not depend on the caller's addresses
+        return small_model(xd, td, yd, mask=md, data_info=info, c=xd).cpu()
+
+    small_model.set_cuda_graphs(False)
+    ref1, ref2 = run(x), run(x2)
+    small_model.set_cuda_graphs(True)
+    outs = [run(x) for _ in range(4)]                       # eager, capture + replay, replay, replay
+    assert all(torch.equal(o, ref1) for o in outs)
+    assert torch.equal(run(x2), ref2)                       # same graph, other input values
+    xo, tso, yo, mo, io = weights.make_inputs(1, 32, 32, seed=0, lens=(77,))
+    io = {k: v.to(dev) for k, v in io.items()}
+    other = [small_model(xo.to(dev), tso.to(dev), yo.to(dev), mask=mo.to(dev), data_info=io, c=xo.to(dev)).cpu() for _ in range(3)]
+    assert torch.equal(other[0], other[2])                  # a second key (new caption, new grid) gets its own graph
+    assert torch.equal(run(x), ref1)                        # back to the first key: caption K/V and position table are rebuilt
+    assert torch.equal(run(x2), ref2)
+    plain = small_model(x.to(dev), td, yd, mask=md, data_info=info).cpu()   # c=None is a different key
+    assert torch.equal(small_model(x.to(dev), td, yd, mask=md, data_info=info).cpu(), plain)
+    assert torch.equal(small_model(x.to(dev), td, yd, mask=md, data_info=info).cpu(), plain)
+    assert not torch.equal(plain, ref1)
+
+
 def test_pos_embed_and_forward_c(small_model, golden_dir):
     from oracle import dit_oracle
     dev = _cuda()
