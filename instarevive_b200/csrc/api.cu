@@ -598,6 +598,15 @@ int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* v
   return attention_tc_launch(a, (cudaStream_t)stream);
 }
 
+int ir_debug_gemm_trace(long long* device_buf) {
+  gemm_set_trace(device_buf);
+#ifdef IR_DEBUG
+  return 16;
+#else
+  return 0;   // the release library carries no trace code
+#endif
+}
+
 int ir_debug_attention_trace(long long* device_buf) {
   attention_tc_set_trace(device_buf);
   return attention_tc_trace_len();

@@ -88,7 +88,24 @@ struct GemmDev {
   // EPI_QKV
   bf16 *q_heads, *k_heads, *vt_heads;
   int qkv_T, qkv_Tp, qkv_H, qkv_hd;
+  long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
 };
+
+#ifdef IR_DEBUG
+IR_DEVINL long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define IR_STAMP(slot)                                                                  \
+  do {                                                                                  \
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[slot] = gtimer(); \
+  } while (0)
+#else
+#define IR_STAMP(slot) \
+  do {                 \
+  } while (0)
+#endif
 
 template <int BN, int EPI, bool CONV, int CG>
 __global__ void __launch_bounds__(NUM_THREADS_MAX, 1)
@@ -123,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // compiler wraps every one of them in an elect-one loop (~80 cycles per MMA: more than a 128 x 128 x 16 MMA takes)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  if (warp == 0) IR_STAMP(0);   // kernel entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -156,8 +174,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  if (warp == 0) IR_STAMP(1);   // prologue done
   pdl_wait();
   pdl_launch();
+  if (warp == 0) IR_STAMP(2);   // predecessor complete
 
   const int mb_total = p.m_units * p.batch;
   const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
@@ -244,12 +264,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }   // leader
           __syncwarp();
+          if (tile == unit0 && kb == 0) IR_STAMP(3);   // first stage issued
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
+      IR_STAMP(4);   // producer done
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (convergent warp, one lane issues)
@@ -272,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) IR_STAMP(5);   // first operands landed
           const int TAPS = CONV ? p.ntap : 1;
           if (CG == 1 && p.dbg_nomma) {
             if (leader) {
@@ -313,6 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           }   // leader
           __syncwarp();
+          if (kb == p.k_blocks - 1) IR_STAMP(6 + (it < 3 ? it : 3));   // tile `it` fully issued (slots 6..9)
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -372,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
+      if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));   // accumulator of tile `it` complete (slot 10: first, 11: last seen)
 
       // Residual reads are software-pipelined one 32-column chunk ahead (two chunks of loads in flight per warp): the
       // epilogue is latency-bound on these loads, not bandwidth-bound.
@@ -645,9 +670,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");   // staging is reused by the next tile's first chunk
       }
+      if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));   // epilogue of tile `it` done (12: first, 13: last seen)
     }
   }
 
+  if (warp == 0) IR_STAMP(14);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();   // the peer may still read this CTA's operands / signal its barriers
@@ -658,6 +685,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else
       tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (warp == 0) IR_STAMP(15);   // exit
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -715,6 +743,9 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 }
 
 static int num_sms() { return device_num_sms(); }
+
+static long long* g_gemm_trace = nullptr;
+void gemm_set_trace(long long* device_buf) { g_gemm_trace = device_buf; }
 int gemm_conv_tiles_per_image(int H, int W) { return ((W + CONV_BW - 1) / CONV_BW) * ((H + CONV_BH - 1) / CONV_BH); }
 
 static bool conv_wres_enabled() {
@@ -891,6 +922,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.qkv_Tp = a.qkv_Tp;
   p.qkv_H = a.qkv_H;
   p.qkv_hd = a.qkv_hd;
+  p.trace = g_gemm_trace;
 
   CUtensorMap ta, tw;
   long m_blocks_total;

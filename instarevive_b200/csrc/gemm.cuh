@@ -99,6 +99,9 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+// diagnostics (library built with -DIR_DEBUG only): CTA 0 of every GEMM launch writes %globaltimer stamps of its roles
+// into this device buffer of 16 int64 (tools/gpu_gemm_trace.py); nullptr switches it off
+void gemm_set_trace(long long* device_buf);
 
 // number of kernel launches issued by this library since load (bench.py's gpu_launches counter)
 void count_launch(int n = 1);

@@ -37,6 +37,21 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def _all_gather_equal(pad: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather of equally sized chunks -> (world, *pad.shape). NCCL: one all_gather_into_tensor over NVLink; gloo (the
+    CPU tests, and the single-GPU multi-process tests, where CUDA tensors are staged through the host)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if pad.device.type == "cuda" and dist.get_backend(group) == "nccl":
+        out = torch.empty((world,) + tuple(pad.shape), dtype=pad.dtype, device=pad.device)
+        dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+        return out
+    host = pad.detach().cpu().contiguous()
+    chunks = [torch.empty_like(host) for _ in range(world)]
+    dist.all_gather(chunks, host, group=group)
+    return torch.stack(chunks).to(pad.device)
+
+
 def all_gather_items(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
     """local: (n_local, ...) items owned by this rank under shard_range; returns (n_items, ...) in list order on every
     rank. Pads to equal counts so that a single all_gather_into_tensor (NCCL over NVLink on the GPU box, gloo in the CPU
@@ -48,17 +63,87 @@ def all_gather_items(local: torch.Tensor, n_items: int, group=None) -> torch.Ten
     per = (n_items + world - 1) // world
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    if local.device.type == "cuda":
-        dist.all_gather_into_tensor(out, pad, group=group)
-    else:
-        chunks = list(out.view((world, per) + tuple(local.shape[1:])).unbind(0))
-        dist.all_gather(chunks, pad, group=group)
+    out = _all_gather_equal(pad, group)
     pieces = []
     for r in range(world):
         s, e = shard_range(n_items, r, world)
-        pieces.append(out[r * per: r * per + (e - s)])
+        pieces.append(out[r, : e - s])
     return torch.cat(pieces, dim=0)
+
+
+class TilePlan:
+    """Three-phase schedule of a tiled restore over `world` ranks when the tile count does not divide (25 tiles on 8 GPUs).
+
+    The plain two-phase split (DiT on ceil(nt/world) tiles, all-gather, decode ceil(nt/world) tiles) costs
+    ceil * (t_dit + t_dec): the ranks with the extra tile are the critical path of BOTH phases. Here
+      phase 1  every rank runs the DiT on `base` = nt // world tiles (contiguous in list order); all-gather A;
+      phase 2  the `rem` = nt % world ranks that own a left-over ("late") tile run the DiT on it, while every other rank
+               already decodes one tile whose latent window overlaps no late tile (so its blended latent is final after
+               A); all-gather B moves the late latents;
+      phase 3  the remaining tiles are decoded, split evenly in list order; all-gather C; pixel blend.
+    i.e. base * t_dit + max(t_dit, t_dec) + ceil((nt - early) / world) * t_dec  --  3 d + 4 v instead of 4 d + 4 v for 25
+    tiles on 8 ranks. Every tile's DiT and decode results are independent of the batch they run in, and both blends add
+    tiles in list order, so the image is bit-identical to the single-rank one for every world size."""
+
+    def __init__(self, windows, world: int):
+        nt = len(windows)
+        self.nt, self.world = nt, world
+        self.base, self.rem = divmod(nt, world)
+        self.three_phase = world > 1 and self.rem > 0 and self.base > 0
+        self.late = list(range(self.base * world, nt)) if self.three_phase else []
+
+        def overlaps(a, b):
+            return a[0] < b[1] and b[0] < a[1] and a[2] < b[3] and b[2] < a[3]
+
+        free = [t for t in range(nt) if t not in self.late and not any(overlaps(windows[t], windows[l]) for l in self.late)]
+        # phase 2: rank r >= rem decodes free[r - rem] (ranks without a free tile idle)
+        self.early = {}
+        if self.three_phase:
+            for r in range(self.rem, world):
+                if r - self.rem < len(free):
+                    self.early[r] = free[r - self.rem]
+        taken = set(self.early.values())
+        self.rest = [t for t in range(nt) if t not in taken]   # phase 3, list order
+
+    def dit_tiles(self, rank):
+        """(phase-1 tiles, phase-2 late tile or None)"""
+        if not self.three_phase:
+            s, e = shard_range(self.nt, rank, self.world)
+            return list(range(s, e)), None
+        first = list(range(rank * self.base, (rank + 1) * self.base))
+        return first, (self.late[rank] if rank < self.rem else None)
+
+    def decode_tiles(self, rank):
+        """(phase-2 early tile or None, phase-3 tiles)"""
+        if not self.three_phase:
+            s, e = shard_range(self.nt, rank, self.world)
+            return None, list(range(s, e))
+        s, e = shard_range(len(self.rest), rank, self.world)
+        return self.early.get(rank), self.rest[s:e]
+
+    def decode_owner_order(self):
+        """For all-gather C: per rank the tile ids in the order the rank stacks them (early tile first), and the padded
+        per-rank slot count."""
+        lists = []
+        for r in range(self.world):
+            early, rest = self.decode_tiles(r)
+            lists.append(([early] if early is not None else []) + rest)
+        return lists, max(len(l) for l in lists)
+
+
+def gather_decoded_tiles(plan: "TilePlan", mine: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather C of the three-phase plan: `mine` = this rank's decoded tiles stacked in plan order (early tile first,
+    then its phase-3 tiles); returns all nt tiles in list order on every rank."""
+    lists, per = plan.decode_owner_order()
+    pad = torch.zeros((per,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    pad[: mine.shape[0]] = mine
+    got = _all_gather_equal(pad, group)
+    got = got.view((plan.world * per,) + tuple(mine.shape[1:]))
+    slot = [0] * plan.nt
+    for r, ids in enumerate(lists):
+        for k, t in enumerate(ids):
+            slot[t] = r * per + k
+    return got.index_select(0, torch.tensor(slot, device=mine.device))
 
 
 def _dist_info(group=None):
@@ -219,43 +304,79 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
     th = tw = tile_size // 8
     windows = _sliding_windows(h, w, th, tile_stride // 8)
     nt = len(windows)
-    coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=control.device)
-    s, e = shard_range(nt, rank, world)
-    mine = coords[s:e].contiguous()
-    # loop 1 (inference.py:128-134): all my tiles as one DiT batch (sample-major inside each tile)
-    if e > s:
-        tiles_in = tile_gather(init_noise.contiguous(), mine, th, tw, 1)              # (k,N,4,th,tw)
-        x0 = generate_sample_1step(model, scheduler, tiles_in.view(-1, 4, th, tw), 400, _tile_captions(y, n, e - s),
-                                   _tile_captions(y_mask, n, e - s), use_control=use_control)
-        x0 = x0.view(e - s, n, 4, th, tw)
-    else:
-        x0 = torch.empty(0, n, 4, th, tw, device=control.device)
+    dev = control.device
+    coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=dev)
+    plan = TilePlan(windows, world)
+    init_noise = init_noise.contiguous()
+    control = control.contiguous()
+
+    def dit_on(ids):
+        """loop 1 (inference.py:128-134) for the tiles `ids` as ONE DiT batch (sample-major inside each tile)"""
+        if not ids:
+            return torch.empty(0, n, 4, th, tw, device=dev)
+        cc = coords[torch.tensor(ids, device=dev)].contiguous() if ids != list(range(ids[0], ids[-1] + 1)) else coords[ids[0]:ids[-1] + 1].contiguous()
+        tiles_in = tile_gather(init_noise, cc, th, tw, 1)                             # (k,N,4,th,tw)
+        x0 = generate_sample_1step(model, scheduler, tiles_in.view(-1, 4, th, tw), 400, _tile_captions(y, n, len(ids)),
+                                   _tile_captions(y_mask, n, len(ids)), use_control=use_control)
+        return x0.view(len(ids), n, 4, th, tw)
+
+    def decode_on(ids, latent):
+        """loop 2 (inference.py:139-152) for the tiles `ids`: decode + colour fix, in balanced chunks of at most
+        decode_batch tiles (25 tiles -> 7+6+6+6 rather than 8+8+8+1: a lone tile would run the decoder in its small-M
+        regime); per-tile results do not depend on the chunking (bit-identical)"""
+        if not ids:
+            return torch.empty(0, n, 3, 8 * th, 8 * tw, device=dev)
+        cap = max(1, decode_batch)
+        n_chunks = (len(ids) + cap - 1) // cap
+        outs = []
+        for i in range(n_chunks):
+            b0, b1 = shard_range(len(ids), i, n_chunks)
+            cc = coords[torch.tensor(ids[b0:b1], device=dev)].contiguous()
+            zt = tile_gather(latent, cc, th, tw, 1).view(-1, 4, th, tw)
+            ti = vae.decode_tensor(zt, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)   # (k*N,3,8th,8tw)
+            if color_fix_type in ("wavelet", "adain"):
+                cond = tile_gather(control, cc, 8 * th, 8 * tw, 8).view(-1, 3, 8 * th, 8 * tw)
+                ti = wavelet_reconstruction(ti, cond) if color_fix_type == "wavelet" else adaptive_instance_normalization(ti, cond)
+            outs.append(ti.view(b1 - b0, n, 3, 8 * th, 8 * tw))
+        return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+    first, late = plan.dit_tiles(rank)
+    x0 = dit_on(first)
     _mark(timer, "dit")
-    if world > 1:
-        x0 = all_gather_items(x0, nt, group)                                          # all-gather #1: tile latents
-    _mark(timer, "allgather_latents")
-    noise_buffer = tile_blend(x0, coords, h, w, 1)                                    # inference.py:133-136
-    _mark(timer, "latent_blend")
-    # loop 2 (inference.py:139-152): decode + colour-fix my tiles, blend in pixel space
-    outs = []
-    # balanced decode chunks of at most decode_batch tiles (25 tiles -> 7+6+6+6 rather than 8+8+8+1: a lone tile would
-    # run the decoder in its small-M regime); per-tile results do not depend on the chunking (bit-identical)
-    n_mine, cap = e - s, max(1, decode_batch)
-    n_chunks = (n_mine + cap - 1) // cap
-    bounds = [s + shard_range(n_mine, i, n_chunks)[0] for i in range(n_chunks)] + [e]
-    for b0, b1 in zip(bounds[:-1], bounds[1:]):
-        cc = coords[b0:b1].contiguous()
-        zt = tile_gather(noise_buffer, cc, th, tw, 1).view(-1, 4, th, tw)
-        ti = vae.decode_tensor(zt, in_scale=1.0 / sf, out_scale=0.5, out_shift=0.5)   # (k*N,3,8th,8tw)
-        if color_fix_type in ("wavelet", "adain"):
-            cond = tile_gather(control.contiguous(), cc, 8 * th, 8 * tw, 8).view(-1, 3, 8 * th, 8 * tw)
-            ti = wavelet_reconstruction(ti, cond) if color_fix_type == "wavelet" else adaptive_instance_normalization(ti, cond)
-        outs.append(ti.view(b1 - b0, n, 3, 8 * th, 8 * tw))
-    tiles_px = torch.cat(outs, dim=0) if outs else torch.empty(0, n, 3, 8 * th, 8 * tw, device=control.device)
-    _mark(timer, "decode_colorfix")
-    if world > 1:
-        tiles_px = all_gather_items(tiles_px, nt, group)                              # all-gather #2: decoded tiles
-    _mark(timer, "allgather_pixels")
+    if not plan.three_phase:
+        if world > 1:
+            x0 = all_gather_items(x0, nt, group)                                      # all-gather #1: tile latents
+        _mark(timer, "allgather_latents")
+        noise_buffer = tile_blend(x0, coords, h, w, 1)                                # inference.py:133-136
+        _mark(timer, "latent_blend")
+        _, mine = plan.decode_tiles(rank)
+        tiles_px = decode_on(mine, noise_buffer)
+        _mark(timer, "decode_colorfix")
+        if world > 1:
+            tiles_px = all_gather_items(tiles_px, nt, group)                          # all-gather #2: decoded tiles
+        _mark(timer, "allgather_pixels")
+    else:
+        # ---- phase 1 -> 2: all-gather A of the `base` tiles per rank (list order), partial blend (final wherever no late
+        # tile reaches), then the late DiT tiles on the ranks that own one while the others decode their early tile
+        n_a = plan.base * world
+        x0_a = _all_gather_equal(x0, group).view(n_a, n, 4, th, tw)
+        _mark(timer, "allgather_latents")
+        partial = tile_blend(x0_a, coords[:n_a].contiguous(), h, w, 1)
+        _mark(timer, "latent_blend")
+        early, rest = plan.decode_tiles(rank)
+        x0_late = dit_on([late]) if late is not None else torch.zeros(1, n, 4, th, tw, device=dev)
+        px_early = decode_on([early], partial) if early is not None else None
+        _mark(timer, "late_dit_or_early_decode")
+        x0_b = _all_gather_equal(x0_late, group)[: plan.rem, 0]                        # all-gather B: the late latents
+        _mark(timer, "allgather_latents")
+        noise_buffer = tile_blend(torch.cat([x0_a, x0_b], dim=0), coords, h, w, 1)    # inference.py:133-136
+        _mark(timer, "latent_blend")
+        # ---- phase 3: the remaining decodes, split evenly in list order
+        px_rest = decode_on(rest, noise_buffer)
+        mine_px = px_rest if px_early is None else torch.cat([px_early, px_rest], dim=0)
+        _mark(timer, "decode_colorfix")
+        tiles_px = gather_decoded_tiles(plan, mine_px, group)                         # all-gather C: decoded tiles
+        _mark(timer, "allgather_pixels")
     img = tile_blend(tiles_px, coords, height, width, 8)                              # inference.py:151-153
     _mark(timer, "pixel_blend")
     return (img, noise_buffer) if return_latents else img
