@@ -266,9 +266,16 @@ def run_cuda(args):
         raise RuntimeError("bench.py needs a CUDA device: the restoration path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The contract is ONE JSON line on stdout. NCCL (and anything else native) may announce itself on file descriptor 1, so
+    # the real stdout is set aside and fd 1 points at stderr until rank 0 writes the line through the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if world > 1:
-        # NCCL announces its version on stdout when NCCL_DEBUG is VERSION (some images export that); the contract is ONE
-        # JSON line on stdout, so keep warnings only
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
@@ -325,7 +332,7 @@ def run_cuda(args):
     if args.only_tiled:   # development aid: just the tiled_2048 block (strong scaling), one JSON line
         blk = run_tiled_block(args, ir, pipeline, weights, net, vae, sched, y, mask, dev, world, rank, timed, crc_of, load_images)
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "n_gpus": world, "tiled_2048": blk}), flush=True)
+            emit({"metric": METRIC, "n_gpus": world, "tiled_2048": blk})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -452,7 +459,7 @@ def run_cuda(args):
             "side_measurements": side_info, "tiled_2048": tiled_block,
             "mfu_vs_measured_peak": (exec_step / (total_ms / steps / 1e3) / 1e12 / peak_tf) if exec_step else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -83,13 +83,19 @@ class TilePlan:
       phase 3  the remaining tiles are decoded, split evenly in list order; all-gather C; pixel blend.
     i.e. base * t_dit + max(t_dit, t_dec) + ceil((nt - early) / world) * t_dec  --  3 d + 4 v instead of 4 d + 4 v for 25
     tiles on 8 ranks. Every tile's DiT and decode results are independent of the batch they run in, and both blends add
-    tiles in list order, so the image is bit-identical to the single-rank one for every world size."""
+    tiles in list order, so the image is bit-identical to the single-rank one for every world size.
 
-    def __init__(self, windows, world: int):
+    MEASURED on 8 B200 (profiles/r02_tiled_n8_*.json): 20.11 ms against 20.30 ms for the two-phase split -- a wash. At 3-4
+    tiles per rank the DiT forward is bound by per-kernel latency, not by FLOPs (t_dit(b) ~ 4.9 + 1.0 b ms: the fourth
+    tile costs 1 ms, a separate one-tile forward 4.4 ms), so trading the extra DiT tile for an extra phase buys nothing,
+    and at 2 / 4 ranks the model says it loses. restore_latents therefore defaults to the two-phase split
+    (tile_plan="contiguous"); tile_plan="overlap" selects this schedule (overlap=False here = the two-phase plan)."""
+
+    def __init__(self, windows, world: int, overlap: bool = True):
         nt = len(windows)
         self.nt, self.world = nt, world
         self.base, self.rem = divmod(nt, world)
-        self.three_phase = world > 1 and self.rem > 0 and self.base > 0
+        self.three_phase = overlap and world > 1 and self.rem > 0 and self.base > 0
         self.late = list(range(self.base * world, nt)) if self.three_phase else []
 
         def overlaps(a, b):
@@ -275,7 +281,7 @@ def _mark(timer, name):
 def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor, y, y_mask, *, tiled: bool,
                     tile_size: int = 512, tile_stride: int = 448, color_fix_type: str = "wavelet", scheduler=None,
                     decode_batch: int = 8, group=None, return_latents: bool = False, distributed: bool = True,
-                    use_control: bool = False, timer: Optional[PhaseTimer] = None):
+                    use_control: bool = False, timer: Optional[PhaseTimer] = None, tile_plan: str = "contiguous"):
     """Everything of process() between VAE-encode and the uint8 conversion (inference.py:111-153), on the GPU.
     control: (N,3,H,W) in [0,1]; init_noise: (N,4,H/8,W/8). Returns the fp32 image buffer (N,3,H,W) [and latents].
     use_control=False (default) is the reference's literal call, generate_sample_1step(model, ..., c=None)
@@ -306,7 +312,9 @@ def restore_latents(model, vae, control: torch.Tensor, init_noise: torch.Tensor,
     nt = len(windows)
     dev = control.device
     coords = torch.tensor([(c[0], c[2]) for c in windows], dtype=torch.int32, device=dev)
-    plan = TilePlan(windows, world)
+    if tile_plan not in ("contiguous", "overlap"):
+        raise ValueError(f"tile_plan must be 'contiguous' or 'overlap', got {tile_plan!r}")
+    plan = TilePlan(windows, world, overlap=tile_plan == "overlap")
     init_noise = init_noise.contiguous()
     control = control.contiguous()
 
