@@ -286,6 +286,9 @@ def run_cuda(args):
     net.load_state_dict(weights.make_dit_state_dict(depth=depth, copy_blocks=cb, seed=1), strict=True)
     net = net.to(dev)
     net.pack()
+    if args.plain_schedule:   # profiling aid: one stream, program order, no graph (ncu launch lists joined by launch order)
+        net.set_cuda_graphs(False)
+        net.set_dual_chain(False)
     # encoder + decoder on this repo's own kernels: nothing from cuDNN / ATen convolutions runs in any timed region
     vae = ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=dev)
     sched = ir.DDPMSchedulerLite()
@@ -527,6 +530,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true", help="skip the VAE-encoder / SwinIR side measurements and e2e_full_cli")
     ap.add_argument("--dump-shapes", default=None, help="write the per-launch shape list of one profiled step (JSON) here")
+    ap.add_argument("--plain-schedule", action="store_true", help="profiling aid: no CUDA graph, no second stream")
     ap.add_argument("--only-tiled", action="store_true", help="development aid: run only the tiled_2048 block")
     ap.add_argument("--no-tiled", action="store_true", help="skip the tiled_2048 block (BASELINE configs[3])")
     args = ap.parse_args()

@@ -92,6 +92,10 @@ int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l);
  * captures the forward, later calls replay it (inputs / output are staged through fixed buffers of the workspace).
  * enable = 0 switches back to plain stream-ordered launches and drops the cached graphs. */
 int ir_dit_set_graphs(ir_dit* h, int enable);
+/* Dual-chain schedule (default on): the ControlNet chain (pixart_controlnet.py:238-240: controlnet[i] depends on the base
+ * chain only through block 0) runs on a second stream ahead of the base chain, one event per control block. enable = 0
+ * launches everything on the caller's stream in program order (profilers that join launches by order want that). */
+int ir_dit_set_dual_chain(ir_dit* h, int enable);
 /*
  * x, c: (B,4,H,W) fp32 latents (c may be NULL: plain 28-block path); timestep: (B) fp32;
  * y: (rows,4096) fp32 caption embeddings; y_index: device int32 (sum_l) valid rows of y, sample-major;

@@ -226,6 +226,15 @@ int ir_dit_set_graphs(ir_dit* h, int enable) {
   return IR_OK;
 }
 
+int ir_dit_set_dual_chain(ir_dit* h, int enable) {
+  if (!h) {
+    set_last_error("ir_dit_set_dual_chain: null handle");
+    return IR_ERR_INVALID;
+  }
+  dit_set_dual_chain(h->d, enable != 0);
+  return IR_OK;
+}
+
 int ir_dit_reserve(ir_dit* h, int max_tokens, int max_sum_l) {
   if (!h) {
     set_last_error("ir_dit_reserve: null handle");

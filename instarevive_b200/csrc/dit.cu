@@ -527,7 +527,7 @@ static int dit_forward_body(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   int next = 1;
   if (a.c) {
     const int ncb = d->cfg.copy_blocks;
-    const bool dual = dual_chain_enabled() && !prof_enabled() && ncb > 0;
+    const bool dual = d->dual_chain && dual_chain_enabled() && !prof_enabled() && ncb > 0;
     cudaStream_t cs_stream = s;
     if (dual) {
       IR_TRY(ensure_side_stream(d));
@@ -708,6 +708,11 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
   count_launch(hit->launches);
   IR_CUDA_CHECK(cudaMemcpyAsync(a.out, w.g_out, px * d->cfg.out_ch * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return IR_OK;
+}
+
+void dit_set_dual_chain(Dit* d, bool on) {
+  if (d->dual_chain != on) destroy_graphs(d);   // cached graphs embody the other schedule
+  d->dual_chain = on;
 }
 
 void dit_set_graphs(Dit* d, bool on) {

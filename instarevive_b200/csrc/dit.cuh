@@ -87,6 +87,7 @@ struct Dit {
   cudaStream_t side = nullptr;       // control-chain stream of the dual-chain schedule (created on first use)
   cudaEvent_t ev_fork = nullptr;     // base block 0 done -> the control chain may start
   std::vector<cudaEvent_t> ev_c;     // [copy_blocks] control block i done -> the base chain may inject c_i
+  bool dual_chain = true;            // control chain on a second stream (dit_forward); off = one stream, program order
   bool graphs_enabled = true;        // replay the forward as a CUDA graph from the third call with a key on
   std::vector<DitGraph> graphs;
   cudaStream_t cap_stream = nullptr; // capture happens on this stream (the caller's may be the uncapturable legacy stream)
@@ -126,6 +127,7 @@ int dit_forward(Dit* d, const DitForwardArgs& a, cudaStream_t s);
 // caption tokens) so that no forward allocates
 int dit_reserve(Dit* d, int max_tokens, int max_sum_l);
 void dit_set_graphs(Dit* d, bool on);
+void dit_set_dual_chain(Dit* d, bool on);
 int dit_patch_embed(Dit* d, const float* x, float* tokens, int B, int H, int W, cudaStream_t s);
 
 }  // namespace ir

@@ -466,12 +466,18 @@ int xattention_tc_launch(const XAttnTcArgs& a, cudaStream_t stream) {
   auto launch = [&](auto kern) -> int {
     IR_TRY(ensure_smem_optin((const void*)kern, SMEM_MAX));
     // resident CTAs per SM: registers / shared memory (occupancy query) and TMEM columns
-    static int occ_cache[32] = {};   // per instantiation (static of this generic lambda), indexed by Lp / 16: the query costs microseconds
+    static int occ_cache[32] = {};   // per instantiation (static of this generic lambda), indexed by Lp / 16
     int& occ_c = occ_cache[(p.Lp / 16) & 31];
     if (occ_c == 0) {
-      int o = 1;
-      IR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, XNTHREADS, (size_t)smem));
-      occ_c = o < 1 ? 1 : o;
+      // resident CTAs per SM from the kernel's own attributes (64 K registers allocated per warp in units of 256, 228 KB of
+      // shared memory with 1 KB reserved per CTA); cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 here on B200
+      cudaFuncAttributes fa;
+      IR_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+      const int regs_cta = ((fa.numRegs * 32 + 255) / 256 * 256) * (XNTHREADS / 32);
+      const int by_regs = 65536 / (regs_cta > 0 ? regs_cta : 1);
+      const int by_smem = (228 * 1024) / (smem + 1024);
+      int o = by_regs < by_smem ? by_regs : by_smem;
+      occ_c = o < 1 ? 1 : (o > 16 ? 16 : o);
     }
     int occ = occ_c;
     const int by_tmem = 512 / p.tmem_cols;

@@ -279,6 +279,11 @@ class ControlPixArtMSHalf(nn.Module):
         self.pack()
         _lib.check(_lib.lib().ir_dit_set_graphs(self._handle, 1 if enable else 0), "ir_dit_set_graphs")
 
+    def set_dual_chain(self, enable: bool) -> None:
+        """Run the ControlNet chain on a second stream ahead of the base chain (default on); off = one stream."""
+        self.pack()
+        _lib.check(_lib.lib().ir_dit_set_dual_chain(self._handle, 1 if enable else 0), "ir_dit_set_dual_chain")
+
     def __del__(self):
         try:
             if getattr(self, "_handle", None):

@@ -53,7 +53,7 @@ def main():
     shapes = json.loads(open(shapes_json).read())
     fam = {"gemm": "gemm_tc_kernel", "conv": "gemm_tc_kernel", "attention": "attn_tc_kernel"}
     s_rows = [s for s in shapes if s["class"] in fam]
-    n_rows = [r for r in ncu if ("gemm_tc_kernel" in r["name"] or "attn_tc_kernel" in r["name"])]
+    n_rows = [r for r in ncu if ("gemm_tc_kernel" in r["name"] or ("attn_tc_kernel" in r["name"] and "xattn" not in r["name"]))]
     if len(s_rows) != len(n_rows):
         sys.exit(f"launch count mismatch: shape log {len(s_rows)} vs ncu {len(n_rows)}")
     agg = OrderedDict()
