@@ -226,8 +226,9 @@ int ir_cross_attention_tc_bf16(const void* q, const void* kv, void* vt_ws, void*
  * instrumented instantiation that records SM-clock stamps of the warp roles of CTA (0,0,0); NULL switches it off. */
 int ir_debug_attention_trace(long long* device_buf);
 /* Diagnostics: in a library built with -DIR_DEBUG, CTA 0 of every tcgen05 GEMM / conv launch writes %globaltimer stamps of
- * its warp roles into device_buf (returned length in int64 elements; 0 = release build, no trace code compiled in). */
-int ir_debug_gemm_trace(long long* device_buf);
+ * its warp roles into record (launch index % slots) of device_buf (slots x 16 int64). Returns the record length in int64
+ * elements (16), or 0 in a release build, which carries no trace code. NULL switches the trace off. */
+int ir_debug_gemm_trace(long long* device_buf, int slots);
 int ir_ln_modulate(const float* x, void* out_bf16, const float* shift, const float* scale, long long mod_stride,
                    int rows, int T, int D, void* stream);
 int ir_pos_embed(float* table, int gh, int gw, int D, int base_size, float pe_interpolation, void* stream);

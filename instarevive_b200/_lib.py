@@ -55,7 +55,7 @@ PROTOTYPES = {
     "ir_cross_attention_vt_bytes": (_sz, [_i, _i]),
     "ir_cross_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),
     "ir_debug_attention_trace": (_i, [_vp]),
-    "ir_debug_gemm_trace": (_i, [_vp]),
+    "ir_debug_gemm_trace": (_i, [_vp, _i]),
     "ir_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ir_pos_embed": (_i, [_vp, _i, _i, _i, _i, _f, _vp]),
     "ir_lincomb3": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),

@@ -607,8 +607,8 @@ int ir_attention_tc_bf16(const void* q_heads, const void* k_heads, const void* v
   return attention_tc_launch(a, (cudaStream_t)stream);
 }
 
-int ir_debug_gemm_trace(long long* device_buf) {
-  gemm_set_trace(device_buf);
+int ir_debug_gemm_trace(long long* device_buf, int slots) {
+  gemm_set_trace(device_buf, slots);
 #ifdef IR_DEBUG
   return 16;
 #else

@@ -107,9 +107,84 @@ IR_DEVINL long long gtimer() {
   } while (0)
 #endif
 
+
+// ---------------------------------------------------------------------------------------------- conv epilogue helpers
+// TMA store / bulk-group primitives and swizzled staging access of the conv epilogue (CONV && EPI_BF16)
+IR_DEVINL void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+IR_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+IR_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+IR_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+IR_DEVINL uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+IR_DEVINL void sts_u4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Sum NV per-lane values over the 32 lanes of a warp with a butterfly reduce-scatter: log2(NV) steps in which partner
+// lanes split the value array (NV/2, NV/4, ... shuffles) followed by plain xor steps on the remaining lane bits --
+// NV - 1 + (5 - log2 NV) shuffles instead of 5 * NV, in a FIXED order (deterministic). Afterwards lane L holds the total
+// of value index idx(L) = the bits (4, 3, ...) of L it used for splitting, most significant first; v[0] is that total.
+template <int NV>
+IR_DEVINL void warp_reduce_scatter(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float give = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+    }
+  }
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+// value index lane L holds after warp_reduce_scatter<NV>, and whether L is the lane that writes it
+template <int NV>
+IR_DEVINL int reduce_scatter_index(int lane, bool& writer) {
+  int idx = 0, bit = 4;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, --bit) idx = (idx << 1) | ((lane >> bit) & 1);
+  writer = (lane & ((1 << (bit + 1)) - 1)) == 0;
+  return idx;
+}
+
+// GroupNorm partials of one 32-column chunk: this thread holds one pixel x 32 consecutive channels (fp32, before the
+// bf16 rounding -- what the reference normalises); CPG channels per group. The warp's 32 pixels are summed in a fixed
+// order and lanes write (sum, sum of squares) of group `g0 + idx / 2` to partial[(slot * 32 + group) * 2 + which].
+template <int CPG>
+IR_DEVINL void gn_chunk_partials(const float (&a)[32], int lane, float* __restrict__ partial, long slot, int g0, bool valid) {
+  constexpr int GPC = 32 / CPG, NV = 2 * GPC;
+  float v[NV];
+#pragma unroll
+  for (int g = 0; g < GPC; ++g) {
+    float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      s_ += a[g * CPG + j];
+      q_ = fmaf(a[g * CPG + j], a[g * CPG + j], q_);
+    }
+    v[2 * g] = s_;
+    v[2 * g + 1] = q_;
+  }
+  warp_reduce_scatter<NV>(v, lane);
+  bool writer;
+  const int idx = reduce_scatter_index<NV>(lane, writer);
+  if (writer && valid) partial[(slot * 32 + g0 + (idx >> 1)) * 2 + (idx & 1)] = v[0];
+}
+
 template <int BN, int EPI, bool CONV, int CG>
 __global__ void __launch_bounds__(NUM_THREADS_MAX, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmDev p) {
   using Cfg = GemmCfg<BN, CG, CONV>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(STAGES >= 2, "tile configuration does not fit a double-buffered pipeline");
@@ -133,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   uint64_t* w_full = bars + 2 * STAGES + 6;   // weight slab landed (resident mode)
-  static_assert((2 * STAGES + 7) * 8 <= Cfg::BAR_BYTES, "barrier block");
+  uint64_t* r_bar = bars + 2 * STAGES + 7;    // [EW] conv epilogue: residual tile of warp w landed
+  static_assert((2 * STAGES + 7 + Cfg::EW) * 8 <= Cfg::BAR_BYTES, "barrier block");
 
   // warp index through a shuffle: provably warp-uniform, so the producer / issuer branches are convergent and the
   // uniform-datapath instructions (UTMALDG, UTCHMMA, UTCBAR) are emitted directly; under a divergent `lane == 0` the
@@ -157,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tempty_bar[i], Cfg::EW * CG);  // epilogue warps of every CTA of the pair release the accumulator
     }
     mbar_init(w_full, CG);
+    for (int i = 0; i < Cfg::EW; ++i) mbar_init(&r_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -357,6 +434,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // fused GroupNorm statistics: per-lane (sum, sum of squares) of its 4 channels per 32-column chunk over the rows of
     // ONE tile, reduced by a fixed shuffle tree and written to the slot of (image, tile, warp). Per-tile partials do not
     // depend on how tiles are scheduled or batched, so the statistics are bit-reproducible for any sharding.
+    if constexpr (CONV && EPI == EPI_BF16) {
+      // -------- conv, bf16 output: TMEM -> registers (one pixel x 32 channels per thread) -> bias / residual / GroupNorm
+      // partials -> bf16 -> this warp's 4 KB staging box in the TMA SWIZZLE_128B layout -> ONE TMA store per 64-channel
+      // box ([64 ch][16 x][2 y]: the warp's TMEM lane quarter is two rows of the 16 x 8 pixel patch). No shared-memory
+      // transpose, no per-row address arithmetic or bounds predicates (the tensor map clips partial tiles and carries the
+      // phase mapping of the upsample-folded convs in its strides), stores drain asynchronously. The residual tile
+      // (ResnetBlock x + h, model.py:151) is fetched by TMA into the same box while the tile's MMAs still run. GroupNorm
+      // partials are per (image, tile, lane quarter): no barrier between the epilogue warps.
+      uint8_t* box = reinterpret_cast<uint8_t*>(staging) + (warp - 4) * 4096;
+      const uint32_t box_s = smem_u32(box);
+      const uint32_t my_row = box_s + (uint32_t)lane * 128u;
+      uint64_t* rb = &r_bar[warp - 4];
+      const bool has_resid = p.resid_bf16 != nullptr;
+      const bool gn_on = p.gn_partial != nullptr;
+      constexpr int PAIRS = BN / 64;   // 64-channel boxes per tile
+      uint32_t rphase = 0;
+      int it = 0;
+      for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
+        const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+        const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
+        const int b = mb / p.m_units;
+        const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        const int ty = m_blk / p.tiles_x, tx = m_blk - ty * p.tiles_x;
+        const int px = tx * CONV_BW, py = ty * CONV_BH + 2 * q;
+        const bool tile_ok = m_blk < p.m_blocks;
+        const long slot = ((long)b * (p.gn_slots_img ? p.gn_slots_img : p.m_blocks) + p.gn_slot_off + m_blk) * 4 + q;
+        if (has_resid && chalf < PAIRS) {   // first box of this warp: prefetch its residual under the tile's mainloop
+          if (lane == 0) {
+            bulk_wait_read();   // the previous store out of this box has been read
+            mbar_arrive_expect_tx(rb, 4096);
+            tma_load_4d(box, &tmR, rb, n_blk * BN + chalf * 64, px, py, b);
+          }
+          __syncwarp();
+        }
+        mbar_wait(&tfull_bar[buf], use & 1);
+        tc_fence_after();
+        if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+        if (chalf >= PAIRS) {   // narrow tiles (BN = 64 with 8 epilogue warps): this warp owns no box, it only releases the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+          }
+          continue;
+        }
+#pragma unroll 1
+        for (int pr = chalf; pr < PAIRS; pr += CSTEP) {
+          const int ch0 = n_blk * BN + pr * 64;
+          const bool last_pair = pr + CSTEP >= PAIRS;
+          if (has_resid) {
+            if (pr != chalf) {
+              if (lane == 0) {
+                bulk_wait_read();
+                mbar_arrive_expect_tx(rb, 4096);
+                tma_load_4d(box, &tmR, rb, ch0, px, py, b);
+              }
+              __syncwarp();
+            }
+            mbar_wait(rb, rphase);
+            rphase ^= 1;
+          } else {
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + pr * 64 + half * 32), v);
+            tmem_ld_wait();
+            if (last_pair && half == 1) {
+              // accumulator fully read: hand the TMEM buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+              }
+            }
+            float a[32];
+            const float* bp = p.bias + ch0 + half * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = (p.bias && ch0 + half * 32 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(bp) + j)
+                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+              a[4 * j] = __uint_as_float(v[4 * j]) * p.alpha + b4.x;
+              a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * p.alpha + b4.y;
+              a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * p.alpha + b4.z;
+              a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * p.alpha + b4.w;
+            }
+            if (has_resid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r4 = lds_u4(my_row + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4));
+                const float2 r0 = unpack_bf16x2(r4.x), r1 = unpack_bf16x2(r4.y), r2 = unpack_bf16x2(r4.z), r3 = unpack_bf16x2(r4.w);
+                a[8 * j] += r0.x; a[8 * j + 1] += r0.y; a[8 * j + 2] += r1.x; a[8 * j + 3] += r1.y;
+                a[8 * j + 4] += r2.x; a[8 * j + 5] += r2.y; a[8 * j + 6] += r3.x; a[8 * j + 7] += r3.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts_u4(my_row + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4),
+                     make_uint4(pack_bf16x2(a[8 * j], a[8 * j + 1]), pack_bf16x2(a[8 * j + 2], a[8 * j + 3]),
+                                pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), pack_bf16x2(a[8 * j + 6], a[8 * j + 7])));
+            if (gn_on) {
+              // pixels outside the image (partial tiles) hold conv results of zero-padded input: they are not part of the
+              // tensor and must not enter the statistics
+              const bool inside = (px + (lane & 15) < p.Wd) && (py + (lane >> 4) < p.H);
+              if (!inside) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = 0.f;
+              }
+              const int g0 = (ch0 + half * 32) / p.gn_cpg;
+              if (p.gn_cpg == 4) gn_chunk_partials<4>(a, lane, p.gn_partial, slot, g0, tile_ok && ch0 + half * 32 < p.N);
+              else if (p.gn_cpg == 8) gn_chunk_partials<8>(a, lane, p.gn_partial, slot, g0, tile_ok && ch0 + half * 32 < p.N);
+              else gn_chunk_partials<16>(a, lane, p.gn_partial, slot, g0, tile_ok && ch0 + half * 32 < p.N);
+            }
+          }
+          fence_proxy_async();   // generic-proxy writes of the box -> async-proxy (TMA) read
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, box, ch0, px, py, b);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+        if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));
+      }
+      if (lane == 0) bulk_wait_all();   // the boxes are in global memory before the CTA retires
+      __syncwarp();
+    } else {
     float gn_s[BN / 32 / CSTEP], gn_q[BN / 32 / CSTEP];
     const bool gn_on = (EPI == EPI_BF16) && p.gn_partial != nullptr;
     int it = 0;
@@ -682,6 +890,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));   // epilogue of tile `it` done (12: first, 13: last seen)
     }
+    }   // !(CONV && EPI_BF16)
   }
 
   if (warp == 0) IR_STAMP(14);
@@ -755,7 +964,12 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 static int num_sms() { return device_num_sms(); }
 
 static long long* g_gemm_trace = nullptr;
-void gemm_set_trace(long long* device_buf) { g_gemm_trace = device_buf; }
+static int g_gemm_trace_slots = 1, g_gemm_trace_next = 0;
+void gemm_set_trace(long long* device_buf, int slots) {
+  g_gemm_trace = device_buf;
+  g_gemm_trace_slots = slots > 0 ? slots : 1;
+  g_gemm_trace_next = 0;
+}
 int gemm_conv_tiles_per_image(int H, int W) { return ((W + CONV_BW - 1) / CONV_BW) * ((H + CONV_BH - 1) / CONV_BH); }
 
 static bool conv_wres_enabled() {
@@ -769,7 +983,8 @@ static bool conv_wres_enabled() {
 }
 
 template <int BN, int EPI, bool CONV, int CG>
-static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p_in, cudaStream_t stream) {
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
+                       const GemmDev& p_in, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG, CONV>;
   constexpr int SMEM_MAX = 227 * 1024;
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
@@ -809,7 +1024,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
   cfg.numAttrs = (CG == 2) ? 2 : 1;
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
+  IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, tr, p));
   if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch), p.M * (CONV ? 1 : p.batch), p.N, p.K);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
@@ -817,13 +1032,14 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const GemmD
 }
 
 template <int BN, bool CONV, int CG>
-static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& p, cudaStream_t s) {
+static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
+                      const GemmDev& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, p, s);
-    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, p, s);
-    case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, p, s);
+    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, to, tr, p, s);
+    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, to, tr, p, s);
+    case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, to, tr, p, s);
     case EPI_QKV:
-      if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, p, s);
+      if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, to, tr, p, s);
       break;
   }
   set_last_error("gemm: unknown epilogue %d", epi);
@@ -932,7 +1148,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.qkv_Tp = a.qkv_Tp;
   p.qkv_H = a.qkv_H;
   p.qkv_hd = a.qkv_hd;
-  p.trace = g_gemm_trace;
+  p.trace = g_gemm_trace ? g_gemm_trace + 16L * (g_gemm_trace_next++ % g_gemm_trace_slots) : nullptr;   // one 16-stamp record per launch
 
   CUtensorMap ta, tw;
   long m_blocks_total;
@@ -1001,21 +1217,40 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     IR_TRY(make_map(&tw, a.W, 3, dims, strides, box));
   }
 
+  // conv with bf16 output: tensor maps of the output (and residual) tiles for the TMA-store epilogue. Box = [64 ch][16 x][2 y]
+  // (one TMEM lane quarter of the 16 x 8 pixel patch); the output mapping (y * o_scale + o_oy, x * o_scale + o_ox) of the
+  // upsample-folded phase convs is carried by the base offset and the strides.
+  CUtensorMap to = ta, tr = ta;
+  if (a.conv && a.epi == EPI_BF16) {
+    IR_REQUIRE(a.ldo_b == a.N && a.N % 8 == 0, "conv: bf16 output must be dense NHWC with Cout %% 8 == 0 (ldo %ld, Cout %d)", a.ldo_b, a.N);
+    IR_REQUIRE((reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.resid_bf16) & 15) == 0,
+               "conv: output / residual must be 16-byte aligned");
+    const uint64_t N = (uint64_t)a.N, oW = (uint64_t)p.oW, oH = (uint64_t)p.oH, sc = (uint64_t)a.o_scale;
+    const uint64_t dims[4] = {N, (uint64_t)a.Wd, (uint64_t)a.H, (uint64_t)a.nimg};
+    const uint64_t strides[3] = {sc * N * 2, sc * oW * N * 2, oH * oW * N * 2};
+    const uint32_t box[4] = {64, (uint32_t)CONV_BW, 2, 1};
+    const long base_off = ((long)a.o_oy * p.oW + a.o_ox) * a.N;
+    IR_TRY(make_map(&to, a.out_bf16 + base_off, 4, dims, strides, box));
+    if (a.resid_bf16) IR_TRY(make_map(&tr, a.resid_bf16 + base_off, 4, dims, strides, box));
+  }
+
   if (a.conv) {
     if (tc.cg == 2) {
-      if (bn == 256) return launch_epi<256, true, 2>(a.epi, ta, tw, p, stream);
-      return launch_epi<128, true, 2>(a.epi, ta, tw, p, stream);
+      if (bn == 256) return launch_epi<256, true, 2>(a.epi, ta, tw, to, tr, p, stream);
+      return launch_epi<128, true, 2>(a.epi, ta, tw, to, tr, p, stream);
     }
-    if (bn == 64) return launch_epi<64, true, 1>(a.epi, ta, tw, p, stream);
-    return launch_epi<128, true, 1>(a.epi, ta, tw, p, stream);
+    if (bn == 64) return launch_epi<64, true, 1>(a.epi, ta, tw, to, tr, p, stream);
+    return launch_epi<128, true, 1>(a.epi, ta, tw, to, tr, p, stream);
   }
   if (tc.cg == 2) {
-    if (bn == 256) return launch_epi<256, false, 2>(a.epi, ta, tw, p, stream);
-    return launch_epi<128, false, 2>(a.epi, ta, tw, p, stream);
+    if (bn == 256) return launch_epi<256, false, 2>(a.epi, ta, tw, to, tr, p, stream);
+    return launch_epi<128, false, 2>(a.epi, ta, tw, to, tr, p, stream);
   }
-  if (bn == 64) return launch_epi<64, false, 1>(a.epi, ta, tw, p, stream);
-  if (bn == 128) return launch_epi<128, false, 1>(a.epi, ta, tw, p, stream);
-  return launch_epi<256, false, 1>(a.epi, ta, tw, p, stream);
+  if (bn == 64) return launch_epi<64, false, 1>(a.epi, ta, tw, to, tr, p, stream);
+  if (bn == 128) return launch_epi<128, false, 1>(a.epi, ta, tw, to, tr, p, stream);
+  return launch_epi<256, false, 1>(a.epi, ta, tw, to, tr, p, stream);
 }
+
+int gemm_conv_gn_slots_per_tile() { return 4; }
 
 }  // namespace ir

@@ -80,6 +80,9 @@ int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
                     const uint32_t* box, int swizzle_bytes);
 int device_num_sms();
 int gemm_conv_tiles_per_image(int H, int W);  // 128-pixel tiles per image of the implicit-GEMM conv
+// GroupNorm partial slots a conv (bf16 output) writes per tile: one per TMEM lane quarter (no barrier between the epilogue
+// warps); partial[(((img * slots_img + slot_off + tile) * 4 + quarter) * 32 + group) * 2]
+int gemm_conv_gn_slots_per_tile();
 
 // Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait()); IR_NO_PDL=1 disables it.
 bool pdl_enabled();
@@ -100,8 +103,8 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
 // diagnostics (library built with -DIR_DEBUG only): CTA 0 of every GEMM launch writes %globaltimer stamps of its roles
-// into this device buffer of 16 int64 (tools/gpu_gemm_trace.py); nullptr switches it off
-void gemm_set_trace(long long* device_buf);
+// into this device buffer of slots x 16 int64, launch i into record i % slots (tools/gpu_gemm_trace.py); nullptr = off
+void gemm_set_trace(long long* device_buf, int slots);
 
 // number of kernel launches issued by this library since load (bench.py's gpu_launches counter)
 void count_launch(int n = 1);

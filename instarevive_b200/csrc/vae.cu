@@ -810,7 +810,7 @@ static size_t vae_carve(const Vae* v, VaeWs& w, void* base, int B, int h, int wd
   w.pm = reinterpret_cast<bf16*>(take((size_t)P * P * sizeof(bf16)));
   w.scores = reinterpret_cast<float*>(take((size_t)P * P * sizeof(float)));
   // GroupNorm partials: standalone pass (<= GN_MAX_CHUNKS chunks) or fused (4 warps x 128-pixel tiles at full resolution)
-  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(8 * h, 8 * wd)) * 64;
+  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(8 * h, 8 * wd) * gemm_conv_gn_slots_per_tile()) * 64;
   w.partial = reinterpret_cast<float*>(take((size_t)w.partial_elems * sizeof(float)));
   w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
   return (off + 255) & ~size_t(255);
@@ -906,7 +906,7 @@ static int conv3x3(VCtx& c, const std::string& name, const bf16* x, bf16* y, con
   g.out_bf16 = y;
   g.resid_bf16 = resid;
   g.ldo_b = Cout;
-  const int nslots = gemm_conv_tiles_per_image(H, W);
+  const int nslots = gemm_conv_tiles_per_image(H, W) * gemm_conv_gn_slots_per_tile();   // one partial per (tile, lane quarter)
   const bool fuse = want_stats && fused_stats_ok(Cout) && (long)c.B * nslots * 64 <= c.w.partial_elems;
   if (fuse) {
     g.gn_partial = c.w.partial;
@@ -924,10 +924,11 @@ static int upsample_conv(VCtx& c, const std::string& name, const bf16* x, bf16* 
   auto up = c.v->up_w.find(name + ".weight");
   IR_REQUIRE(up != c.v->up_w.end(), "upsample_conv: no phase weights for '%s'", name.c_str());
   const int tiles = gemm_conv_tiles_per_image(H, W);
-  const bool fuse = fused_stats_ok(C) && (long)c.B * 4 * tiles * 64 <= c.w.partial_elems;
+  const int per_tile = gemm_conv_gn_slots_per_tile();
+  const bool fuse = fused_stats_ok(C) && (long)c.B * 4 * tiles * per_tile * 64 <= c.w.partial_elems;
   IR_TRY(upsample_conv_phases_launch(x, up->second, vp<float>(c.v, name + ".bias"), y, c.B, H, W, C,
                                      fuse ? c.w.partial : nullptr, 0, c.s));
-  if (fuse) IR_TRY(finish_fused_stats(c, 4 * H * W, C, 4 * tiles));
+  if (fuse) IR_TRY(finish_fused_stats(c, 4 * H * W, C, 4 * tiles * per_tile));
   return IR_OK;
 }
 
@@ -1162,7 +1163,7 @@ static size_t vae_enc_carve(const Vae* v, VaeWs& w, void* base, int B, int H, in
   w.vt = reinterpret_cast<bf16*>(take((size_t)P * C * sizeof(bf16)));
   w.pm = reinterpret_cast<bf16*>(take((size_t)P * P * sizeof(bf16)));
   w.scores = reinterpret_cast<float*>(take((size_t)P * P * sizeof(float)));
-  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(H, W)) * 64;
+  w.partial_elems = (long)B * std::max<long>(GN_MAX_CHUNKS, (long)gemm_conv_tiles_per_image(H, W) * gemm_conv_gn_slots_per_tile()) * 64;
   w.partial = reinterpret_cast<float*>(take((size_t)w.partial_elems * sizeof(float)));
   w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
   w.f32tmp = reinterpret_cast<float*>(take((size_t)B * P * 2 * v->cfg.z_channels * sizeof(float)));
