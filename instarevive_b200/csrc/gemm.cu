@@ -23,7 +23,7 @@ static constexpr int CONV_BH = 8;
 static constexpr int STG_LD = 36;    // staging row stride in floats (32 + 4 pad: conflict-free v4 stores)
 static constexpr int NUM_THREADS_MAX = 384;
 
-template <int BN, int CG, bool CONV>
+template <int BN, int CG, bool CONV, int EPI = EPI_BF16>
 struct GemmCfg {
   // CG = 1: one CTA per 128 x BN tile. CG = 2: a CTA pair (cta_group::2) per 256 x BN tile; each CTA stages its own
   // 128 rows of A and BN/2 rows of B, which halves the L2 -> shared-memory traffic of the B operand per FLOP.
@@ -42,7 +42,12 @@ struct GemmCfg {
   // marginal MMA cost of 158 us per 309 GFLOP on top of ~209 us that does not scale with K (~6500 cycles per tile).
   static constexpr int EW = CONV ? ((BN / CG <= 64) ? 8 : 4) : 8;
   static constexpr int NUM_THREADS = 128 + 32 * EW;
-  static constexpr int STG_BYTES = EW * 32 * STG_LD * 4;
+  // staging per epilogue warp: 4608 B for the transposing epilogues (32 x 36 floats); the row-owner epilogues of the linear
+  // GEMMs stage two 4 KB TMA boxes instead: bf16 outputs ping-pong between two [64 col][32 row] boxes (a box is rewritten
+  // only after the store two boxes back has read it), the fp32-residual epilogue holds the two fp32 [32 col][32 row] boxes
+  // of a column pair; 1024 B aligned (TMA SWIZZLE_128B pattern)
+  static constexpr int STG_WARP = CONV ? 32 * STG_LD * 4 : 8192;
+  static constexpr int STG_BYTES = EW * STG_WARP;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_MAX = (227 * 1024 - 1024 - STG_BYTES - BAR_BYTES) / (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
@@ -88,6 +93,7 @@ struct GemmDev {
   // EPI_QKV
   bf16 *q_heads, *k_heads, *vt_heads;
   int qkv_T, qkv_Tp, qkv_H, qkv_hd;
+  int row_path;       // linear GEMM: row-owner epilogue with TMA-store boxes (host-checked alignment), else the transposing one
   long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
 };
 
@@ -116,8 +122,15 @@ IR_DEVINL void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, 
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+IR_DEVINL void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 IR_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 IR_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+IR_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 IR_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 IR_DEVINL uint4 lds_u4(uint32_t saddr) {
   uint4 v;
@@ -184,8 +197,9 @@ IR_DEVINL void gn_chunk_partials(const float (&a)[32], int lane, float* __restri
 template <int BN, int EPI, bool CONV, int CG>
 __global__ void __launch_bounds__(NUM_THREADS_MAX, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const GemmDev p) {
-  using Cfg = GemmCfg<BN, CG, CONV>;
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmF, const GemmDev p) {
+  using Cfg = GemmCfg<BN, CG, CONV, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(STAGES >= 2, "tile configuration does not fit a double-buffered pipeline");
 
@@ -427,7 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CSTEP = EW / 4;           // warps per TMEM lane quarter = chunk interleave
     const int q = warp & 3;                 // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
     const int chalf = (warp - 4) >> 2;      // which interleaved set of 32-column chunks this warp owns
-    float* stg = staging + (warp - 4) * (32 * STG_LD);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staging) + (warp - 4) * Cfg::STG_WARP);
     const uint32_t stg_s = smem_u32(stg);
     const int col4 = (lane & 7) * 4;
     const int rsub = lane >> 3;
@@ -462,7 +476,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int px = tx * CONV_BW, py = ty * CONV_BH + 2 * q;
         const bool tile_ok = m_blk < p.m_blocks;
         const long slot = ((long)b * (p.gn_slots_img ? p.gn_slots_img : p.m_blocks) + p.gn_slot_off + m_blk) * 4 + q;
-        if (has_resid && chalf < PAIRS) {   // first box of this warp: prefetch its residual under the tile's mainloop
+        const bool box_any = tile_ok && px < p.Wd && py < p.H;   // a box entirely outside the image neither loads nor stores
+        const bool resid_t = has_resid && box_any;
+        if (resid_t && chalf < PAIRS && n_blk * BN + chalf * 64 < p.N) {   // first box of this warp: prefetch its residual under the tile's mainloop
           if (lane == 0) {
             bulk_wait_read();   // the previous store out of this box has been read
             mbar_arrive_expect_tx(rb, 4096);
@@ -485,7 +501,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int pr = chalf; pr < PAIRS; pr += CSTEP) {
           const int ch0 = n_blk * BN + pr * 64;
           const bool last_pair = pr + CSTEP >= PAIRS;
-          if (has_resid) {
+          if (ch0 >= p.N) {   // Cout tail: this 64-channel box does not exist; only the accumulator hand-back remains
+            if (last_pair) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+              }
+            }
+            continue;
+          }
+          if (resid_t) {
             if (pr != chalf) {
               if (lane == 0) {
                 bulk_wait_read();
@@ -524,7 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * p.alpha + b4.z;
               a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * p.alpha + b4.w;
             }
-            if (has_resid) {
+            if (resid_t) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 r4 = lds_u4(my_row + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4));
@@ -554,7 +580,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_proxy_async();   // generic-proxy writes of the box -> async-proxy (TMA) read
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && box_any) {
             tma_store_4d(&tmO, box, ch0, px, py, b);
             bulk_commit();
           }
@@ -565,6 +591,187 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) bulk_wait_all();   // the boxes are in global memory before the CTA retires
       __syncwarp();
     } else {
+    bool row_path_done = false;
+    if constexpr (!CONV && EPI != EPI_QKV) {
+      if (p.row_path) {
+        // -------- linear GEMMs, row-owner epilogue: a thread owns one output row (its TMEM lane) and 32 consecutive columns
+        // per chunk. bf16 outputs: two chunks fill one 128 B row of a [64 col][32 row] box in the TMA SWIZZLE_128B layout and
+        // leave by ONE TMA store per box. fp32-residual epilogue (x += gate * (A W^T + b), PixArtMS.py:71-79): the residual
+        // rows arrive by TMA into two fp32 boxes ([32 col][32 row], fetched while the tile's MMAs still run), are updated in
+        // place and stored back by TMA, the bf16 copy of the new stream leaves through a third box. No shared-memory
+        // transpose, no per-row address arithmetic or predicates (the tensor maps clip the M / N tails), stores drain
+        // asynchronously behind the next chunk.
+        row_path_done = true;
+        constexpr bool F32 = (EPI == EPI_F32);
+        uint8_t* wbase = reinterpret_cast<uint8_t*>(staging) + (warp - 4) * Cfg::STG_WARP;
+        const uint32_t rowf0 = smem_u32(wbase) + (uint32_t)lane * 128u, rowf1 = rowf0 + 4096u;
+        int nbox = 0;   // bf16 outputs: boxes alternate
+        uint64_t* rb = &r_bar[warp - 4];
+        const bool has_resid = F32 && p.resid_f32 != nullptr;
+        const bool want_bf16 = !F32 || p.out_bf16 != nullptr;
+        constexpr int PAIRS = BN / 64;
+        uint32_t rphase = 0;
+        int it = 0;
+        for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
+          const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+          const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
+          const int b = mb / p.m_units;
+          const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          const int row0 = m_blk * BM + q * 32;
+          const bool row_ok = row0 + lane < p.M;   // M tail: rows beyond M are zero-filled on load and clipped on store
+          const int gate_row = row_ok ? (row0 + lane) / p.rows_per_gate : 0;
+          const bool rows_any = row0 < p.M;           // a lane quarter entirely beyond M neither loads nor stores
+          const bool resid_t = has_resid && rows_any;
+          if (resid_t && chalf < PAIRS && n_blk * BN + chalf * 64 < p.N) {   // first column pair of this warp: residual rows fetched under the mainloop
+            if (lane == 0) {
+              const int c0 = n_blk * BN + chalf * 64;
+              const bool two = c0 + 32 < p.N;   // a box that starts beyond N is neither fetched nor stored
+              bulk_wait_read();
+              mbar_arrive_expect_tx(rb, two ? 8192 : 4096);
+              tma_load_3d(wbase, &tmR, rb, c0, row0, b);
+              if (two) tma_load_3d(wbase + 4096, &tmR, rb, c0 + 32, row0, b);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&tfull_bar[buf], use & 1);
+          tc_fence_after();
+          if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+          if (chalf >= PAIRS) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+            }
+            continue;
+          }
+#pragma unroll 1
+          for (int pr = chalf; pr < PAIRS; pr += CSTEP) {
+            const int col0 = n_blk * BN + pr * 64;
+            const bool last_pair = pr + CSTEP >= PAIRS;
+            if (col0 >= p.N) {   // N tail: this column pair does not exist; only the accumulator hand-back remains
+              if (last_pair) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+                }
+              }
+              continue;
+            }
+            if (resid_t) {
+              if (pr != chalf) {
+                if (lane == 0) {
+                  const bool two = col0 + 32 < p.N;
+                  bulk_wait_read();
+                  mbar_arrive_expect_tx(rb, two ? 8192 : 4096);
+                  tma_load_3d(wbase, &tmR, rb, col0, row0, b);
+                  if (two) tma_load_3d(wbase + 4096, &tmR, rb, col0 + 32, row0, b);
+                }
+                __syncwarp();
+              }
+              mbar_wait(rb, rphase);
+              rphase ^= 1;
+            } else {
+              if (lane == 0) {
+                if (F32) bulk_wait_read(); else bulk_wait_read1();   // bf16: only the store two boxes back must have drained
+              }
+              __syncwarp();
+            }
+            uint8_t* boxb = wbase + (nbox & 1) * 4096;
+            const uint32_t rowb = smem_u32(boxb) + (uint32_t)lane * 128u;
+            ++nbox;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t v[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + pr * 64 + half * 32), v);
+              tmem_ld_wait();
+              if (last_pair && half == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+                }
+              }
+              const int colh = col0 + half * 32;
+              const float* bp = p.bias + (long)b * p.stride_bias + colh;
+              const float* gp = p.gate + (long)gate_row * p.gate_ld + colh;
+              const uint32_t rowf = half ? rowf1 : rowf0;
+              float a[32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool cok = colh + 4 * j < p.N;
+                const float4 b4 = (p.bias && cok) ? __ldg(reinterpret_cast<const float4*>(bp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float x0 = __uint_as_float(v[4 * j]) * p.alpha + b4.x, x1 = __uint_as_float(v[4 * j + 1]) * p.alpha + b4.y;
+                float x2 = __uint_as_float(v[4 * j + 2]) * p.alpha + b4.z, x3 = __uint_as_float(v[4 * j + 3]) * p.alpha + b4.w;
+                if (EPI == EPI_BF16_GELU) {
+                  if (p.gelu_erf) {   // exact GELU (nn.GELU default: SwinIR's Mlp); warp-uniform branch
+                    x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));
+                    x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
+                    x2 = 0.5f * x2 * (1.0f + erff(x2 * 0.70710678118654752f));
+                    x3 = 0.5f * x3 * (1.0f + erff(x3 * 0.70710678118654752f));
+                  } else {            // tanh approximation (PixArt's Mlp, approximate="tanh")
+                    x0 = gelu_tanh_fast(x0);
+                    x1 = gelu_tanh_fast(x1);
+                    x2 = gelu_tanh_fast(x2);
+                    x3 = gelu_tanh_fast(x3);
+                  }
+                }
+                if (F32) {
+                  if (p.gate) {
+                    const float4 g4 = cok ? __ldg(reinterpret_cast<const float4*>(gp) + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    x0 *= g4.x; x1 *= g4.y; x2 *= g4.z; x3 *= g4.w;
+                  }
+                  const uint32_t sa = rowf + (uint32_t)((j ^ (lane & 7)) << 4);
+                  if (resid_t) {
+                    const float4 r4 = lds_f4(sa);
+                    x0 += r4.x; x1 += r4.y; x2 += r4.z; x3 += r4.w;
+                  }
+                  sts_f4(sa, make_float4(x0, x1, x2, x3));
+                }
+                a[4 * j] = x0; a[4 * j + 1] = x1; a[4 * j + 2] = x2; a[4 * j + 3] = x3;
+              }
+              if (want_bf16) {
+                if (F32) {
+                  // bf16 copy of the updated stream (next GEMM's A operand): 64 contiguous bytes of this thread's row
+                  if (row_ok) {
+                    bf16* ob = p.out_bf16 + (long)b * p.stride_ob + (long)(row0 + lane) * p.ldo_b + colh;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      if (colh + 8 * j < p.N)
+                        *reinterpret_cast<uint4*>(ob + 8 * j) =
+                            make_uint4(pack_bf16x2(a[8 * j], a[8 * j + 1]), pack_bf16x2(a[8 * j + 2], a[8 * j + 3]),
+                                       pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), pack_bf16x2(a[8 * j + 6], a[8 * j + 7]));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    sts_u4(rowb + (uint32_t)(((half * 4 + j) ^ (lane & 7)) << 4),
+                           make_uint4(pack_bf16x2(a[8 * j], a[8 * j + 1]), pack_bf16x2(a[8 * j + 2], a[8 * j + 3]),
+                                      pack_bf16x2(a[8 * j + 4], a[8 * j + 5]), pack_bf16x2(a[8 * j + 6], a[8 * j + 7])));
+                }
+              }
+            }
+            fence_proxy_async();   // generic-proxy writes of the boxes -> async-proxy (TMA) reads
+            __syncwarp();
+            if (lane == 0 && rows_any) {
+              if (F32) {
+                tma_store_3d(&tmF, wbase, col0, row0, b);
+                if (col0 + 32 < p.N) tma_store_3d(&tmF, wbase + 4096, col0 + 32, row0, b);
+              }
+              if (!F32) tma_store_3d(&tmO, boxb, col0, row0, b);
+              bulk_commit();
+            }
+            __syncwarp();
+          }
+          if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));
+        }
+        if (lane == 0) bulk_wait_all();
+        __syncwarp();
+      }
+    }
+    if (!row_path_done) {
     float gn_s[BN / 32 / CSTEP], gn_q[BN / 32 / CSTEP];
     const bool gn_on = (EPI == EPI_BF16) && p.gn_partial != nullptr;
     int it = 0;
@@ -876,7 +1083,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int w = 0; w < 4; ++w) {
                 float a0, a1;
                 asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0), "=f"(a1)
-                             : "r"(stg0 + (uint32_t)((owner * 4 + w) * 32 * STG_LD * 4 + gi * 8)) : "memory");
+                             : "r"(stg0 + (uint32_t)((owner * 4 + w) * Cfg::STG_WARP + gi * 8)) : "memory");
                 s_ += a0;
                 q_ += a1;
               }
@@ -890,6 +1097,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));   // epilogue of tile `it` done (12: first, 13: last seen)
     }
+    }   // !row_path_done
     }   // !(CONV && EPI_BF16)
   }
 
@@ -926,7 +1134,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map, innermost dimension first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_bytes) {
+                    const uint32_t* box, int swizzle_bytes, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
@@ -941,7 +1149,7 @@ int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
                                      : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B),
@@ -963,6 +1171,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 
 static int num_sms() { return device_num_sms(); }
 
+static constexpr int ROW_PATH_DEFAULT = 1;   // measured on B200: plain bf16 gains (qkv-like 29.3 -> 27.4 us), GELU and fp32-residual lose (34.9 -> 40.8, 18.1 -> 22.6 us)
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_slots = 1, g_gemm_trace_next = 0;
 void gemm_set_trace(long long* device_buf, int slots) {
@@ -984,8 +1193,8 @@ static bool conv_wres_enabled() {
 
 template <int BN, int EPI, bool CONV, int CG>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
-                       const GemmDev& p_in, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG, CONV>;
+                       const CUtensorMap& tf, const GemmDev& p_in, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CG, CONV, EPI>;
   constexpr int SMEM_MAX = 227 * 1024;
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
   IR_TRY(ensure_smem_optin((const void*)kern, CONV ? SMEM_MAX : Cfg::SMEM_BYTES));
@@ -1024,7 +1233,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   cfg.numAttrs = (CG == 2) ? 2 : 1;
   const bool prof = prof_enabled();
   if (prof) prof_before(stream);
-  IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, tr, p));
+  IR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, tr, tf, p));
   if (prof) prof_after(stream, CONV ? PROF_CONV : PROF_GEMM, 2.0 * (double)p.M * p.N * p.K * (CONV ? 1 : p.batch), p.M * (CONV ? 1 : p.batch), p.N, p.K);
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
@@ -1033,13 +1242,13 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
 
 template <int BN, bool CONV, int CG>
 static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const CUtensorMap& tr,
-                      const GemmDev& p, cudaStream_t s) {
+                      const CUtensorMap& tf, const GemmDev& p, cudaStream_t s) {
   switch (epi) {
-    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, to, tr, p, s);
-    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, to, tr, p, s);
-    case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, to, tr, p, s);
+    case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, to, tr, tf, p, s);
+    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, to, tr, tf, p, s);
+    case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, to, tr, tf, p, s);
     case EPI_QKV:
-      if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, to, tr, p, s);
+      if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, to, tr, tf, p, s);
       break;
   }
   set_last_error("gemm: unknown epilogue %d", epi);
@@ -1234,21 +1443,56 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (a.resid_bf16) IR_TRY(make_map(&tr, a.resid_bf16 + base_off, 4, dims, strides, box));
   }
 
+  // linear GEMMs: tensor maps of the row-owner epilogue (bf16 box [64 col][32 row], fp32 boxes [32 col][32 row]) when the
+  // outputs meet TMA's alignment rules; otherwise the transposing epilogue serves the launch
+  CUtensorMap tf = ta;
+  p.row_path = 0;
+  if (!a.conv && a.epi != EPI_QKV && !a.resid_bf16 && !a.gn_partial) {
+    const bool f32 = a.epi == EPI_F32;
+    const bool want_b = !f32 || a.out_bf16 != nullptr;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool ok = true;
+    if (want_b) ok = ok && al16(a.out_bf16) && a.ldo_b % 8 == 0 && (a.batch == 1 || a.stride_ob % 8 == 0);
+    if (f32) ok = ok && al16(a.out_f32) && al16(a.resid_f32) && a.ldo_f % 4 == 0 && (a.batch == 1 || a.stride_of % 4 == 0);
+    if (ok) {
+      const uint64_t dims[3] = {(uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.batch};
+      if (want_b) {
+        const uint64_t st[2] = {(uint64_t)a.ldo_b * 2, (uint64_t)(a.batch > 1 ? a.stride_ob : (long)a.M * a.ldo_b) * 2};
+        const uint32_t box[3] = {64, 32, 1};
+        IR_TRY(make_map(&to, a.out_bf16, 3, dims, st, box));
+      }
+      if (f32) {
+        const uint64_t st[2] = {(uint64_t)a.ldo_f * 4, (uint64_t)(a.batch > 1 ? a.stride_of : (long)a.M * a.ldo_f) * 4};
+        const uint32_t box[3] = {32, 32, 1};
+        IR_TRY(make_tensor_map(&tf, a.out_f32, 3, dims, st, box, 128, 4));
+        if (a.resid_f32) IR_TRY(make_tensor_map(&tr, a.resid_f32, 3, dims, st, box, 128, 4));
+      }
+      // which epilogues take the row-owner path: bit 0 plain bf16, bit 1 GELU, bit 2 fp32-residual (IR_GEMM_ROWPATH: A/B
+      // switch of debug builds)
+      static const int row_mask = [] {
+        const char* e = debug_env("IR_GEMM_ROWPATH");
+        return e ? atoi(e) : ROW_PATH_DEFAULT;
+      }();
+      const int bit = a.epi == EPI_BF16 ? 1 : (a.epi == EPI_BF16_GELU ? 2 : 4);
+      p.row_path = (row_mask & bit) ? 1 : 0;
+    }
+  }
+
   if (a.conv) {
     if (tc.cg == 2) {
-      if (bn == 256) return launch_epi<256, true, 2>(a.epi, ta, tw, to, tr, p, stream);
-      return launch_epi<128, true, 2>(a.epi, ta, tw, to, tr, p, stream);
+      if (bn == 256) return launch_epi<256, true, 2>(a.epi, ta, tw, to, tr, tf, p, stream);
+      return launch_epi<128, true, 2>(a.epi, ta, tw, to, tr, tf, p, stream);
     }
-    if (bn == 64) return launch_epi<64, true, 1>(a.epi, ta, tw, to, tr, p, stream);
-    return launch_epi<128, true, 1>(a.epi, ta, tw, to, tr, p, stream);
+    if (bn == 64) return launch_epi<64, true, 1>(a.epi, ta, tw, to, tr, tf, p, stream);
+    return launch_epi<128, true, 1>(a.epi, ta, tw, to, tr, tf, p, stream);
   }
   if (tc.cg == 2) {
-    if (bn == 256) return launch_epi<256, false, 2>(a.epi, ta, tw, to, tr, p, stream);
-    return launch_epi<128, false, 2>(a.epi, ta, tw, to, tr, p, stream);
+    if (bn == 256) return launch_epi<256, false, 2>(a.epi, ta, tw, to, tr, tf, p, stream);
+    return launch_epi<128, false, 2>(a.epi, ta, tw, to, tr, tf, p, stream);
   }
-  if (bn == 64) return launch_epi<64, false, 1>(a.epi, ta, tw, to, tr, p, stream);
-  if (bn == 128) return launch_epi<128, false, 1>(a.epi, ta, tw, to, tr, p, stream);
-  return launch_epi<256, false, 1>(a.epi, ta, tw, to, tr, p, stream);
+  if (bn == 64) return launch_epi<64, false, 1>(a.epi, ta, tw, to, tr, tf, p, stream);
+  if (bn == 128) return launch_epi<128, false, 1>(a.epi, ta, tw, to, tr, tf, p, stream);
+  return launch_epi<256, false, 1>(a.epi, ta, tw, to, tr, tf, p, stream);
 }
 
 int gemm_conv_gn_slots_per_tile() { return 4; }

@@ -77,7 +77,7 @@ struct GemmArgs {
 // bf16 tiled tensor map (innermost dimension first; strides in bytes for dims 1..rank-1; zero OOB fill).
 // swizzle_bytes: 128 or 32 (the inner box extent must equal it), or 0 = no swizzle (inner box extent a multiple of 16 B).
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_bytes);
+                    const uint32_t* box, int swizzle_bytes, int elem_bytes = 2);   // elem_bytes: 2 = bf16, 4 = fp32
 int device_num_sms();
 int gemm_conv_tiles_per_image(int H, int W);  // 128-pixel tiles per image of the implicit-GEMM conv
 // GroupNorm partial slots a conv (bf16 output) writes per tile: one per TMEM lane quarter (no barrier between the epilogue
