@@ -809,12 +809,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 
-      mbar_wait(&tfull_bar[buf], use & 1);
-      tc_fence_after();
-      if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));   // accumulator of tile `it` complete (slot 10: first, 11: last seen)
-
       // Residual reads are software-pipelined one 32-column chunk ahead (two chunks of loads in flight per warp): the
-      // epilogue is latency-bound on these loads, not bandwidth-bound.
+      // epilogue is latency-bound on these loads, not bandwidth-bound. The first chunk's residual is requested BEFORE the
+      // wait for the accumulator, so its latency runs under the tile's own MMAs (each output element is read and written
+      // by the same thread of the same tile, so nothing this load can see is still to be written).
       float4 res_cur[8], res_nxt[8];
       uint2 resb_cur[8], resb_nxt[8];
       auto load_resid = [&](int cc, float4 (&r4)[8], uint2 (&rb)[8]) {
@@ -835,6 +833,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       if (EPI == EPI_F32 || EPI == EPI_BF16) load_resid(chalf, res_cur, resb_cur);
       const bool gate_uniform = gate_row[0] == gate_row[7];
+
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));   // accumulator of tile `it` complete (slot 10: first, 11: last seen)
 
       // generic path: the accumulator chunk of the NEXT iteration is requested from TMEM as soon as the current one has
       // been parked in shared memory, so that its latency runs under the current chunk's math and stores
