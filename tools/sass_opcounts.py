@@ -37,7 +37,7 @@ def main():
     cols = KEYS + ["UTCHMMA.2CTA", "UTMALDG.2CTA"]
     print("kernel".ljust(72) + "total".rjust(8) + "".join(c.rjust(14) for c in cols))
     for name, c in sorted(funcs.items(), key=lambda kv: -kv[1]["UTCHMMA"] * 100000 - kv[1]["_total"]):
-        short = re.sub(r"\(.*", "", name).replace("void ", "").replace("ir::", "")
+        short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "")).replace("void ", "").replace("ir::", "")
         print(short[:71].ljust(72) + str(c["_total"]).rjust(8) + "".join(str(c[k]).rjust(14) for k in cols))
         total.update(c)
     print("TOTAL".ljust(72) + str(total["_total"]).rjust(8) + "".join(str(total[k]).rjust(14) for k in cols))
