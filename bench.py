@@ -57,6 +57,13 @@ def _peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _burst_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()).get("bf16_tflops", 1619.3)
+    return 1619.3
+
+
 def _traffic_from_profiles():
     """DRAM traffic of the gemm_tc_kernel family from the committed `ncu --set full` capture of one 1024x1024 step
     (profiles/r02_gemm_traffic_by_shape.json, written by tools/ncu_traffic_by_shape.py from the ncu CSV joined with the
@@ -422,7 +429,13 @@ def run_cuda(args):
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_by_shape": by_shape, "peak_source": peak_src,
                 "launches": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
-                "share_of_step": g_ms / steps / (total_ms / steps)}
+                "share_of_step": g_ms / steps / (total_ms / steps),
+                "peak_burst": _burst_peak(), "frac_of_burst": ach / _burst_peak(),
+                "note": "achieved = algorithmic FLOPs of the family's launches / their summed CUDA-event durations, from a pass that "
+                        "runs the step single-stream without the CUDA graph (a kernel's duration is then its own). `peak` is the "
+                        "SUSTAINED cuBLAS figure (what a kernel inside a long step can hold under the power cap); individual "
+                        "shapes in `by_shape` -- the MMA-bound decoder convs -- run in boost-clock windows between lighter kernels "
+                        "and can exceed it, never `peak_burst`"}
     roofline["by_shape"] = by_shape_live
     kernels = {k: {"ms_per_step": v[0] / steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12) if v[0] > 0 else None,
                    "launches_per_step": v[2] / steps} for k, v in prof.items()}
