@@ -68,6 +68,10 @@ struct GemmDev {
   // conv geometry
   int H, Wd, tiles_x, c_blocks;
   int ntap, off_y, off_x;          // taps per axis (3 or 2), halo origin offset
+  int s2;                          // single-tap stages: one pipeline stage = (channel chunk, tap), A = ONE [8][16]-pixel box.
+                                   // Serves the stride-2 3x3 conv (pad right / bottom; the box is gathered at pixel stride 2
+                                   // by the tensor map's elementStrides) and 1x1 convs on the conv epilogue
+  int tap_w, tap_stride;           // single-tap stages: taps per axis (3 or 1), source pixel = stride * (y, x) + (ky, kx)
   int o_scale, o_oy, o_ox, oH, oW; // output pixel mapping (phase of an upsample-folded conv)
   int gn_slot_off, gn_slots_img;
   int wres;      // conv, weight-resident mode: number of A stages (0 = off); the whole per-CTA weight slab stays in smem
@@ -93,6 +97,11 @@ struct GemmDev {
   // EPI_QKV
   bf16 *q_heads, *k_heads, *vt_heads;
   int qkv_T, qkv_Tp, qkv_H, qkv_hd;
+  // EPI_ATTN (row-owner epilogue only): 1 = per-(row, 64-column pair) maxima of acc, no matrix output; 2 = out_bf16 =
+  // exp2(alpha * acc - att_row[row]) + per-(row, pair) sums; 3 = out_bf16 = acc * att_row[row]. att_out[pair * M + row]
+  int att_mode;
+  const float* att_row;
+  float* att_out;
   int row_path;       // linear GEMM: row-owner epilogue with TMA-store boxes (host-checked alignment), else the transposing one
   long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
 };
@@ -113,6 +122,12 @@ IR_DEVINL long long gtimer() {
   } while (0)
 #endif
 
+
+IR_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // ---------------------------------------------------------------------------------------------- conv epilogue helpers
 // TMA store / bulk-group primitives and swizzled staging access of the conv epilogue (CONV && EPI_BF16)
@@ -315,7 +330,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) {
           // conv: one halo box + ntap weight tiles per stage (ntap = 3, or 2 for an upsample-folded phase conv)
-          const uint32_t stage_tx = CONV ? (uint32_t)(Cfg::A_BYTES + (wres ? 0 : p.ntap * Cfg::B_TAP_BYTES))
+          const uint32_t stage_tx = CONV ? (p.s2 ? (uint32_t)(BM * BK * 2 + Cfg::B_TAP_BYTES)
+                                                 : (uint32_t)(Cfg::A_BYTES + (wres ? 0 : p.ntap * Cfg::B_TAP_BYTES)))
                                          : (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES);
           if (CG == 2) {
             if (cta_rank == 0)
@@ -325,7 +341,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           }
-          if (CONV) {
+          if (CONV && p.s2) {
+            // single-tap stage kb = (channel chunk cb, tap). Stride-2 conv: source pixel (2 y + ky, 2 x + kx), pixels beyond
+            // the right / bottom edge (the reference's F.pad(x, (0,1,0,1))) are zero-filled by the TMA unit. 1x1 conv: one tap
+            const int ntaps = p.tap_w * p.tap_w;
+            const int cb = kb / ntaps;
+            const int tap = kb - cb * ntaps;
+            const int ky = tap / p.tap_w, kx = tap - ky * p.tap_w;
+            const int kcol = (tap * p.c_blocks + cb) * BK;
+            const int sx = p.tap_stride * tx * CONV_BW + kx, sy = p.tap_stride * ty * CONV_BH + ky;
+            if (CG == 2) {
+              tma_load_4d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, sx, sy, b);
+              tma_load_3d_2sm(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
+            } else {
+              tma_load_4d(smA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], cb * BK, sx, sy, b);
+              tma_load_3d(smB + stage * Cfg::B_BYTES, &tmW, &full_bar[stage], kcol, n_row0, 0);
+            }
+          } else if (CONV) {
             // stage kb = (channel chunk cb, kx): one halo box + the ky weight tiles
             const int cb = kb / p.ntap;
             const int kx = kb - cb * p.ntap;
@@ -386,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (it == 0 && kb == 0) IR_STAMP(5);   // first operands landed
-          const int TAPS = CONV ? p.ntap : 1;
+          const int TAPS = CONV ? (p.s2 ? 1 : p.ntap) : 1;
           if (CG == 1 && p.dbg_nomma) {
             if (leader) {
               mbar_arrive(&empty_bar[stage]);
@@ -624,6 +656,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int gate_row = row_ok ? (row0 + lane) / p.rows_per_gate : 0;
           const bool rows_any = row0 < p.M;           // a lane quarter entirely beyond M neither loads nor stores
           const bool resid_t = has_resid && rows_any;
+          float att_r = 0.f;   // EPI_ATTN: this row's shift (mode 2) or scale (mode 3)
+          if (EPI == EPI_ATTN && p.att_row && row_ok) att_r = __ldg(p.att_row + row0 + lane);
           if (resid_t && chalf < PAIRS && n_blk * BN + chalf * 64 < p.N) {   // first column pair of this warp: residual rows fetched under the mainloop
             if (lane == 0) {
               const int c0 = n_blk * BN + chalf * 64;
@@ -682,6 +716,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* boxb = wbase + (nbox & 1) * 4096;
             const uint32_t rowb = smem_u32(boxb) + (uint32_t)lane * 128u;
             ++nbox;
+            float att_acc = (EPI == EPI_ATTN && p.att_mode == 1) ? -INFINITY : 0.f;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t v[32];
@@ -699,6 +734,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float* gp = p.gate + (long)gate_row * p.gate_ld + colh;
               const uint32_t rowf = half ? rowf1 : rowf0;
               float a[32];
+              if constexpr (EPI == EPI_ATTN) {
+                // AttnBlock softmax (model.py:195-197) split over three GEMM passes; columns beyond N do not exist
+                if (p.att_mode == 1) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (colh + j < p.N) att_acc = fmaxf(att_acc, __uint_as_float(v[j]));
+                } else if (p.att_mode == 2) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const float e = (colh + j < p.N) ? ex2_approx(fmaf(__uint_as_float(v[j]), p.alpha, -att_r)) : 0.f;
+                    att_acc += e;
+                    a[j] = e;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) * att_r;
+                }
+              } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const bool cok = colh + 4 * j < p.N;
@@ -732,7 +785,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 a[4 * j] = x0; a[4 * j + 1] = x1; a[4 * j + 2] = x2; a[4 * j + 3] = x3;
               }
-              if (want_bf16) {
+              }   // !EPI_ATTN
+              if (want_bf16 && !(EPI == EPI_ATTN && p.att_mode == 1)) {
                 if (F32) {
                   // bf16 copy of the updated stream (next GEMM's A operand): 64 contiguous bytes of this thread's row
                   if (row_ok) {
@@ -753,9 +807,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
+            if (EPI == EPI_ATTN && p.att_mode != 3 && row_ok) p.att_out[(long)(col0 >> 6) * p.M + row0 + lane] = att_acc;
             fence_proxy_async();   // generic-proxy writes of the boxes -> async-proxy (TMA) reads
             __syncwarp();
-            if (lane == 0 && rows_any) {
+            if (lane == 0 && rows_any && !(EPI == EPI_ATTN && p.att_mode == 1)) {
               if (F32) {
                 tma_store_3d(&tmF, wbase, col0, row0, b);
                 if (col0 + 32 < p.N) tma_store_3d(&tmF, wbase + 4096, col0 + 32, row0, b);
@@ -1136,7 +1191,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map, innermost dimension first; strides in bytes for dims 1..rank-1; 128B swizzle, zero OOB fill.
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_bytes, int elem_bytes) {
+                    const uint32_t* box, int swizzle_bytes, int elem_bytes, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
@@ -1148,7 +1203,7 @@ int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
@@ -1205,7 +1260,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   int smem_bytes = Cfg::SMEM_BYTES;
   p.wres = 0;
   p.w_tiles = 0;
-  if (CONV && p.n_blocks == 1 && conv_wres_enabled()) {
+  if (CONV && !p.s2 && p.n_blocks == 1 && conv_wres_enabled()) {
     // weight-resident mode: the CTA's slab of ntap^2 * c_blocks weight tiles beside >= 3 A stages, and enough tiles per
     // persistent CTA to amortise loading it
     const long slab = (long)p.ntap * p.ntap * p.c_blocks * Cfg::B_TAP_BYTES;
@@ -1251,6 +1306,9 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, con
     case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, to, tr, tf, p, s);
     case EPI_QKV:
       if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, to, tr, tf, p, s);
+      break;
+    case EPI_ATTN:
+      if (!CONV) return launch_inst<BN, EPI_ATTN, false, CG>(ta, tw, to, tr, tf, p, s);
       break;
   }
   set_last_error("gemm: unknown epilogue %d", epi);
@@ -1311,6 +1369,12 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     IR_REQUIRE(a.qkv_hd % 4 == 0 && (a.qkv_H * a.qkv_hd) % 32 == 0 && a.N == 3 * a.qkv_H * a.qkv_hd && a.qkv_T > 0 &&
                    a.M % a.qkv_T == 0 && a.qkv_Tp >= a.qkv_T,
                "gemm: EPI_QKV shape mismatch");
+  } else if (a.epi == EPI_ATTN) {
+    IR_REQUIRE(!a.conv && a.batch == 1 && a.att_mode >= 1 && a.att_mode <= 3 && !a.bias && !a.resid_bf16 && !a.gn_partial,
+               "gemm: EPI_ATTN is a plain single-batch GEMM without bias / residual / statistics");
+    IR_REQUIRE(a.att_mode == 1 || (a.out_bf16 && a.ldo_b % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0),
+               "gemm: EPI_ATTN modes 2, 3 need a 16-byte aligned out_bf16 with ld %% 8 == 0");
+    IR_REQUIRE((a.att_mode == 3 || a.att_out) && (a.att_mode == 1 || a.att_row), "gemm: EPI_ATTN row vectors missing");
   } else if (a.epi == EPI_F32) {
     IR_REQUIRE(a.out_f32 && a.ldo_f % 4 == 0, "gemm: EPI_F32 needs out_f32 with ld %% 4 == 0");
     IR_REQUIRE(!a.out_bf16 || a.ldo_b % 4 == 0, "gemm: bf16 copy needs ld %% 4 == 0");
@@ -1338,6 +1402,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.dbg_nomma = nomma;
   }
   p.gelu_erf = a.gelu_erf;
+  p.att_mode = a.att_mode;
+  p.att_row = a.att_row;
+  p.att_out = a.att_out;
   p.out_bf16 = a.out_bf16;
   p.resid_bf16 = a.resid_bf16;
   p.ldo_b = a.ldo_b;
@@ -1364,11 +1431,14 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap ta, tw;
   long m_blocks_total;
   if (a.conv) {
-    IR_REQUIRE(a.C % BK == 0, "conv: C=%d must be a multiple of %d", a.C, BK);
-    IR_REQUIRE(a.conv_taps == 3 || a.conv_taps == 2, "conv: %d taps per axis unsupported", a.conv_taps);
+    IR_REQUIRE(a.C % BK == 0 || (a.conv_taps == 1 && a.C < BK && a.C % 8 == 0), "conv: C=%d must be a multiple of %d", a.C, BK);
+    IR_REQUIRE(a.conv_taps == 3 || a.conv_taps == 2 || a.conv_taps == 1, "conv: %d taps per axis unsupported", a.conv_taps);
     IR_REQUIRE(a.K == a.conv_taps * a.conv_taps * a.C, "conv: K=%d must equal taps^2*C=%d", a.K, a.conv_taps * a.conv_taps * a.C);
     IR_REQUIRE(a.o_scale >= 1 && a.o_oy >= 0 && a.o_oy < a.o_scale && a.o_ox >= 0 && a.o_ox < a.o_scale, "conv: bad output mapping");
     IR_REQUIRE(a.M == a.nimg * a.H * a.Wd, "conv: M mismatch");
+    IR_REQUIRE(a.conv_stride == 1 || (a.conv_stride == 2 && a.conv_taps == 3 && a.o_scale == 1),
+               "conv: stride %d unsupported (1, or 2 with a 3x3 kernel)", a.conv_stride);
+    IR_REQUIRE(a.conv_taps != 1 || a.o_scale == 1, "conv: a 1x1 conv has no output mapping");
     IR_REQUIRE(a.batch == 1, "conv: batch must be 1 (images are folded into M)");
     p.H = a.H;
     p.Wd = a.Wd;
@@ -1376,7 +1446,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     const int tiles_y = (a.H + CONV_BH - 1) / CONV_BH;
     p.m_blocks = p.tiles_x * tiles_y;
     p.batch = a.nimg;  // one "batch" entry per image
-    p.c_blocks = a.C / BK;
+    p.c_blocks = (a.C + BK - 1) / BK;   // C < 64 (1x1 only): one chunk, the TMA unit zero-fills channels C..63
     p.ntap = a.conv_taps;
     p.off_y = a.conv_off_y;
     p.off_x = a.conv_off_x;
@@ -1388,13 +1458,29 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.gn_slot_off = a.gn_slot_off;
     p.gn_slots_img = a.gn_slots_img;
     p.k_blocks = p.ntap * p.c_blocks;   // pipeline steps: (channel chunk, kx), ntap ky taps each
+    p.s2 = (a.conv_stride == 2 || a.conv_taps == 1) ? 1 : 0;
+    p.tap_w = a.conv_taps;
+    p.tap_stride = a.conv_stride;
+    if (p.s2) p.k_blocks = p.tap_w * p.tap_w * p.c_blocks;   // (channel chunk, ky, kx), one tap each
     // the conv epilogue indexes the output by pixel; batch strides are folded into the pixel index
     p.stride_ob = 0;
     p.stride_of = 0;
     const uint64_t dims[4] = {(uint64_t)a.C, (uint64_t)a.Wd, (uint64_t)a.H, (uint64_t)a.nimg};
     const uint64_t strides[3] = {(uint64_t)a.C * 2, (uint64_t)a.Wd * a.C * 2, (uint64_t)a.H * a.Wd * a.C * 2};
     const uint32_t box[4] = {(uint32_t)BK, (uint32_t)CONV_BW, (uint32_t)(CONV_BH + 2), 1};   // halo box: ky = 0..2
-    IR_TRY(make_map(&ta, a.A, 4, dims, strides, box));
+    if (p.s2) {
+      // (H, Wd) is the OUTPUT grid; the input is (st*H, st*Wd). The box names the traversed extent: at element stride 2,
+      // 32 x 16 source pixels land as a dense [8][16]-pixel tile (tools/probes/tma_elem_stride_probe.cu: 16384 B completed,
+      // row (i, j) = pixel (y0 + 2i, x0 + 2j), zero fill beyond the edges)
+      const uint64_t st = (uint64_t)a.conv_stride;
+      const uint64_t dims2[4] = {(uint64_t)a.C, (uint64_t)a.Wd * st, (uint64_t)a.H * st, (uint64_t)a.nimg};
+      const uint64_t strides2[3] = {(uint64_t)a.C * 2, (uint64_t)a.Wd * st * a.C * 2, (uint64_t)a.H * st * a.Wd * st * a.C * 2};
+      const uint32_t box2[4] = {(uint32_t)BK, (uint32_t)(st * CONV_BW), (uint32_t)(st * CONV_BH), 1};
+      const uint32_t es2[4] = {1, (uint32_t)st, (uint32_t)st, 1};
+      IR_TRY(make_tensor_map(&ta, a.A, 4, dims2, strides2, box2, 128, 2, es2));
+    } else {
+      IR_TRY(make_map(&ta, a.A, 4, dims, strides, box));
+    }
     m_blocks_total = (long)p.m_blocks * a.nimg;
   } else {
     IR_REQUIRE(a.lda % 8 == 0 && a.strideA % 8 == 0, "gemm: lda/strideA must be multiples of 8 elements");
@@ -1410,7 +1496,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
   const long m_pairs = (p.m_blocks + 1) / 2;
-  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, a.conv ? p.ntap * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
+  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, (a.conv && !p.s2) ? p.ntap * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
   if (a.conv && tc.cg == 1 && tc.bn == 256) tc.bn = 128;
   const int bn = tc.bn;
   p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;
@@ -1451,7 +1537,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   p.row_path = 0;
   if (!a.conv && a.epi != EPI_QKV && !a.resid_bf16 && !a.gn_partial) {
     const bool f32 = a.epi == EPI_F32;
-    const bool want_b = !f32 || a.out_bf16 != nullptr;
+    const bool want_b = (!f32 || a.out_bf16 != nullptr) && !(a.epi == EPI_ATTN && a.att_mode == 1);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     bool ok = true;
     if (want_b) ok = ok && al16(a.out_bf16) && a.ldo_b % 8 == 0 && (a.batch == 1 || a.stride_ob % 8 == 0);
@@ -1477,8 +1563,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       }();
       const int bit = a.epi == EPI_BF16 ? 1 : (a.epi == EPI_BF16_GELU ? 2 : 4);
       p.row_path = (row_mask & bit) ? 1 : 0;
+      if (a.epi == EPI_ATTN) p.row_path = 1;   // the only epilogue that implements it
     }
   }
+  IR_REQUIRE(a.epi != EPI_ATTN || p.row_path, "gemm: EPI_ATTN needs the row-owner epilogue");
 
   if (a.conv) {
     if (tc.cg == 2) {

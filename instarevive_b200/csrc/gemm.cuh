@@ -10,6 +10,7 @@ enum GemmEpilogue {
   EPI_F32 = 2,        // out_f32 = resid_f32 + gate * (alpha*acc + bias); optional bf16 copy of out_f32
   EPI_QKV = 3,        // attn.qkv projection scattered head-major for the tcgen05 attention kernel:
                       //   q, k -> [B][H][T][hd] bf16, v -> transposed [B][H][hd][Tp] bf16 (acc + bias)
+  EPI_ATTN = 4,       // the passes of a materialised single-head attention (VAE AttnBlock, model.py:181-205), see att_mode
 };
 
 // C[b][m][n] = sum_k A[b][m][k] * W[b][n][k]   (both operands K-major bf16, fp32 accumulation in TMEM).
@@ -56,6 +57,13 @@ struct GemmArgs {
   int gn_cpg = 0;
   int gn_rows_per_img = 0;
 
+  // EPI_ATTN only. att_mode 1: no matrix output, att_out[pair * M + row] = max of acc over the 64-column pair `pair` of the
+  // row. att_mode 2: out_bf16 = exp2(alpha * acc - att_row[row]) and att_out[pair * M + row] = the fp32 sum of those
+  // exponentials over the pair. att_mode 3: out_bf16 = acc * att_row[row]. att_out holds ceil(N / 64) * M floats.
+  int att_mode = 0;
+  const float* att_row = nullptr;
+  float* att_out = nullptr;
+
   // EPI_QKV only: N = 3*H*hd, rows are (b, t) with T tokens per sample
   bf16* q_heads = nullptr;
   bf16* k_heads = nullptr;
@@ -66,6 +74,11 @@ struct GemmArgs {
   // 2x2 conv on the low-resolution input, K = 4*C). conv_off_*: halo origin (source pixel = output pixel + off + tap).
   // Output pixel (y, x) is stored at (y * o_scale + o_oy, x * o_scale + o_ox) of an (H * o_scale) x (Wd * o_scale) image.
   int conv_taps = 3;
+  // conv_taps 1: a 1x1 conv on the NHWC activation (K = C; C < 64 allowed when C % 8 == 0) -- same arithmetic as a plain
+  // GEMM, but on the conv epilogue (pixel-owner threads, TMA-store boxes, per-tile GroupNorm partials).
+  // conv_stride 2 (3x3 only): Downsample's stride-2 conv with zero padding on the right / bottom (model.py:92-101).
+  // (H, Wd) name the OUTPUT grid, the input activation is (2H, 2Wd); source pixel = (2y + ky, 2x + kx).
+  int conv_stride = 1;
   int conv_off_y = -1, conv_off_x = -1;
   int o_scale = 1, o_oy = 0, o_ox = 0;
   // fused GroupNorm statistics of a conv: partial slot = img * gn_slots_img + gn_slot_off + tile (0 = tiles per image)
@@ -77,7 +90,9 @@ struct GemmArgs {
 // bf16 tiled tensor map (innermost dimension first; strides in bytes for dims 1..rank-1; zero OOB fill).
 // swizzle_bytes: 128 or 32 (the inner box extent must equal it), or 0 = no swizzle (inner box extent a multiple of 16 B).
 int make_tensor_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int swizzle_bytes, int elem_bytes = 2);   // elem_bytes: 2 = bf16, 4 = fp32
+                    const uint32_t* box, int swizzle_bytes, int elem_bytes = 2,   // elem_bytes: 2 = bf16, 4 = fp32
+                    const uint32_t* elem_strides = nullptr);   // traversal stride per dimension (nullptr = 1): the box then
+                                                               // names the traversed extent, ceil(box / stride) elements land
 int device_num_sms();
 int gemm_conv_tiles_per_image(int H, int W);  // 128-pixel tiles per image of the implicit-GEMM conv
 // GroupNorm partial slots a conv (bf16 output) writes per tile: one per TMEM lane quarter (no barrier between the epilogue

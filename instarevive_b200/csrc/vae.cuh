@@ -40,6 +40,8 @@ struct Vae {
   // decoder.conv_out as a tap-response GEMM: (32, C) bf16 weight rows [tap*3 + o][c] (rows 27..31 zero) and the bias
   bf16* co_w = nullptr;
   float* co_b = nullptr;
+  // encoder.conv_in as an im2col GEMM: (ch, 32) bf16 weight rows, column (ky*3+kx)*3 + c (columns 27..31 zero)
+  bf16* ci_w = nullptr;
   // decoder.up.N.upsample.conv folded with the nearest x2 upsample: per conv four phase matrices (Cout, 2, 2, Cin) bf16
   std::unordered_map<std::string, bf16*> up_w;
 };
