@@ -198,6 +198,22 @@ int ir_gemm_bf16(const void* A, const void* W, const float* bias, int M, int N, 
 int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
                     void* out_bf16, float* out_f32, const void* resid_bf16, const float* resid_f32, int force_bn,
                     void* stream);
+/* Downsample.forward (ldm/modules/diffusionmodules/model.py:92-101): F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv as an implicit
+ * GEMM (the A tiles are gathered at pixel stride 2 by the TMA unit). act (n,2*Ho,2*Wo,C) NHWC bf16, weight (Cout, 9*C)
+ * tap-major, out (n,Ho,Wo,Cout) NHWC bf16. */
+int ir_conv3x3_s2_bf16(const void* act, const void* weight, const float* bias, int n, int Ho, int Wo, int C, int Cout,
+                       void* out_bf16, int force_bn, void* stream);
+/* 1x1 conv on the conv epilogue (nin_shortcut / proj_out / the gathered taps of Encoder.conv_in, model.py:120-128,
+ * 178-179,456-460): act (n,H,W,C) NHWC bf16 (C a multiple of 64, or a multiple of 8 below 64), weight (Cout, C),
+ * resid_bf16 (optional) and out (n,H,W,Cout) NHWC bf16. */
+int ir_conv1x1_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
+                    void* out_bf16, const void* resid_bf16, int force_bn, void* stream);
+/* One pass of the materialised single-head attention of AttnBlock (model.py:181-205) on the GEMM kernel, acc = A[M,K] W[N,K]^T:
+ * mode 1: att_out[g * M + m] = max of acc over the 64-column group g of row m (no matrix output);
+ * mode 2: out_bf16 = exp2(alpha * acc - att_row[m]), att_out[g * M + m] = fp32 sum of those exponentials over group g;
+ * mode 3: out_bf16 = acc * att_row[m]. att_out holds ceil(N / 64) * M floats; ldo % 8 == 0. */
+int ir_gemm_attn_pass(const void* A, const void* W, int M, int N, int K, long long lda, long long ldw, int mode, float alpha,
+                      const float* att_row, float* att_out, void* out_bf16, long long ldo, int force_bn, void* stream);
 /* Upsample.forward (ldm/modules/diffusionmodules/model.py:63-67): nearest x2 + 3x3 conv (C -> C) as four 2x2 phase convs
  * on the low-resolution input. act (n,H,W,C) NHWC bf16, weight_oihw (C,C,3,3) fp32 in the reference layout, phase_w_ws:
  * 16*C*C bf16 scratch for the pre-summed phase weights, out (n,2H,2W,C) NHWC bf16. */

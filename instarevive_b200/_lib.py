@@ -49,6 +49,9 @@ PROTOTYPES = {
     "ir_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _i, _f, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ir_conv3x3_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "ir_upsample_conv3x3_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "ir_conv3x3_s2_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "ir_conv1x1_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "ir_gemm_attn_pass": (_i, [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _f, _vp, _vp, _vp, _ll, _i, _vp]),
     "ir_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp]),
     "ir_gemm_qkv_heads": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "ir_attention_tc_bf16": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp]),

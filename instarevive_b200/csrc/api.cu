@@ -502,6 +502,74 @@ int ir_conv3x3_bf16(const void* act, const void* weight, const float* bias, int 
   return gemm_launch(g, (cudaStream_t)stream);
 }
 
+int ir_conv3x3_s2_bf16(const void* act, const void* weight, const float* bias, int n, int Ho, int Wo, int C, int Cout,
+                       void* out_bf16, int force_bn, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)act;
+  g.W = (const bf16*)weight;
+  g.ldw = 9L * C;
+  g.M = n * Ho * Wo;
+  g.N = Cout;
+  g.K = 9 * C;
+  g.conv = 1;
+  g.conv_stride = 2;
+  g.nimg = n;
+  g.H = Ho;
+  g.Wd = Wo;
+  g.C = C;
+  g.bias = bias;
+  g.force_bn = force_bn;
+  g.epi = EPI_BF16;
+  g.out_bf16 = (bf16*)out_bf16;
+  g.ldo_b = Cout;
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
+int ir_conv1x1_bf16(const void* act, const void* weight, const float* bias, int n, int H, int W, int C, int Cout,
+                    void* out_bf16, const void* resid_bf16, int force_bn, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)act;
+  g.W = (const bf16*)weight;
+  g.ldw = C;
+  g.M = n * H * W;
+  g.N = Cout;
+  g.K = C;
+  g.conv = 1;
+  g.conv_taps = 1;
+  g.nimg = n;
+  g.H = H;
+  g.Wd = W;
+  g.C = C;
+  g.bias = bias;
+  g.force_bn = force_bn;
+  g.epi = EPI_BF16;
+  g.out_bf16 = (bf16*)out_bf16;
+  g.resid_bf16 = (const bf16*)resid_bf16;
+  g.ldo_b = Cout;
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
+int ir_gemm_attn_pass(const void* A, const void* W, int M, int N, int K, long long lda, long long ldw, int mode, float alpha,
+                      const float* att_row, float* att_out, void* out_bf16, long long ldo, int force_bn, void* stream) {
+  GemmArgs g;
+  g.A = (const bf16*)A;
+  g.lda = lda;
+  g.W = (const bf16*)W;
+  g.ldw = ldw;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = EPI_ATTN;
+  g.att_mode = mode;
+  g.alpha = alpha;
+  g.att_row = att_row;
+  g.att_out = att_out;
+  g.out_bf16 = (bf16*)out_bf16;
+  g.ldo_b = ldo;
+  g.force_bn = force_bn;
+  return gemm_launch(g, (cudaStream_t)stream);
+}
+
 int ir_upsample_conv3x3_bf16(const void* act, const float* weight_oihw, const float* bias, int n, int H, int W, int C,
                              void* phase_w_ws, void* out_bf16, int force_bn, void* stream) {
   if (!act || !weight_oihw || !phase_w_ws || !out_bf16) {

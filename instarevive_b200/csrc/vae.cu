@@ -179,21 +179,26 @@ __global__ void __launch_bounds__(256) gn_finalize_fused_kernel(const float* __r
   pdl_wait();
   pdl_launch();
   double s = 0.0, q = 0.0;
-  const int i1 = min(nslots, (j + 1) * per);
-  for (int i = j * per + warp; i < i1; i += 8) {
-    const float2 pp = *reinterpret_cast<const float2*>(partial + (((long)n * nslots + i) * 32 + lane) * 2);
-    s += (double)pp.x;
-    q += (double)pp.y;
+  const int i0 = j * per, i1 = min(nslots, i0 + per);
+  const float2* base = reinterpret_cast<const float2*>(partial) + (long)n * nslots * 32 + lane;
+  for (int i = i0 + warp; i < i1; i += 64) {   // eight independent 256 B rows in flight per warp
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (i + 8 * u < i1) ? __ldcg(base + (long)(i + 8 * u) * 32) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s += (double)v[u].x;
+      q += (double)v[u].y;
+    }
   }
   red[warp][2 * lane] = s;
   red[warp][2 * lane + 1] = q;
   __syncthreads();
-  double* mine = scratch + ((long)n * NB + j) * 64;
   if (threadIdx.x < 64) {
     double a = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x];
-    if (NB == 1) red[0][threadIdx.x] = a; else mine[threadIdx.x] = a;
+    if (NB == 1) red[0][threadIdx.x] = a; else scratch[((long)n * NB + j) * 64 + threadIdx.x] = a;
   }
   if (NB > 1) {
     __threadfence();
@@ -202,13 +207,25 @@ __global__ void __launch_bounds__(256) gn_finalize_fused_kernel(const float* __r
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x < 64) {
-      double a = 0.0;
-      const volatile double* sc = scratch + (long)n * NB * 64;
-      for (int b = 0; b < NB; ++b) a += sc[b * 64 + threadIdx.x];
-      red[0][threadIdx.x] = a;
+    // the NB block results, four quarters of the block list in parallel, each in index order, quarters combined in order
+    const int v = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int span = (NB + 3) / 4, b0 = part * span, b1 = min(NB, b0 + span);
+    const double* sc = scratch + (long)n * NB * 64 + v;
+    double a = 0.0;
+    for (int b = b0; b < b1; b += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = (b + u < b1) ? __ldcg(sc + (long)(b + u) * 64) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += t[u];
     }
+    __syncthreads();   // everyone is done with red[] of the first stage
+    red[part][v] = a;
+    __syncthreads();
+    if (threadIdx.x < 64) red[4][threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x];
     if (threadIdx.x == 0) count[n] = 0u;
+    __syncthreads();
+    if (threadIdx.x < 64) red[0][threadIdx.x] = red[4][threadIdx.x];
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -815,7 +832,7 @@ struct VaeWs {
 };
 
 static const int GN_MAX_CHUNKS = 2048;
-static const int GN_FIN_BLOCKS = 64;
+static const int GN_FIN_BLOCKS = 256;
 
 static size_t vae_carve(const Vae* v, VaeWs& w, void* base, int B, int h, int wd) {
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
@@ -919,7 +936,7 @@ static int group_norm(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
 
 // After a GEMM / conv launched with fused statistics: reduce the per-(CTA, warp) partials to (mean, rstd).
 static int finish_fused_stats(VCtx& c, int P, int C, int nslots) {
-  int nb = nslots / 128;   // >= 128 slots (32 KB of partials) per block
+  int nb = nslots / 64;   // >= 64 slots (16 KB of partials) per block: one pass of eight 256 B rows per warp
   if (nb > GN_FIN_BLOCKS) nb = GN_FIN_BLOCKS;
   if (nb < 1) nb = 1;
   const int per = (nslots + nb - 1) / nb;

@@ -234,6 +234,34 @@ def _to_host_pair(a: torch.Tensor, b: torch.Tensor):
     return buf[0].numpy().copy(), buf[1].numpy().copy()
 
 
+_pinned_in: dict = {}
+
+
+def _upload_images(control_imgs: Sequence[np.ndarray], device) -> torch.Tensor:
+    """The uint8 HWC images to the device as one (N,H,W,3) tensor through a cached page-locked staging buffer: a pageable
+    source makes cudaMemcpyAsync stage and synchronise inside the driver (measured ~1 ms per 1024^2 image instead of the
+    0.15 ms the 3 MB take over PCIe). The buffer is rewritten only after the previous upload from it has completed."""
+    shape = (len(control_imgs),) + tuple(control_imgs[0].shape)
+    key = (shape, torch.device(device).index)
+    ent = _pinned_in.get(key)
+    if ent is None:
+        if len(_pinned_in) > 4:
+            _pinned_in.clear()
+        ent = _pinned_in[key] = [torch.empty(shape, dtype=torch.uint8, pin_memory=True), None]
+    buf, ev = ent
+    if ev is not None:
+        ev.synchronize()
+    view = buf.numpy()
+    for i, im in enumerate(control_imgs):
+        if im.shape != shape[1:] or im.dtype != np.uint8:
+            raise ValueError("process: control images must be uint8 HWC arrays of equal size")
+        np.copyto(view[i], im)
+    dev_t = buf.to(device, non_blocking=True)
+    ent[1] = torch.cuda.Event()
+    ent[1].record(torch.cuda.current_stream(device))
+    return dev_t
+
+
 _default_scheduler: Optional[DDPMSchedulerLite] = None
 
 
@@ -413,8 +441,7 @@ def process(model, control_imgs: Sequence[np.ndarray], strength: float, color_fi
     # reference: torch.tensor(np.stack(imgs) / 255.0, dtype=float32) on the host (inference.py:92); here the uint8 image
     # is uploaded and divided on the device -- u8/255 in fp32 equals the float64 quotient rounded to fp32 for all 256
     # values (tests/test_host_logic.py), so `control` is bit-identical
-    host = torch.from_numpy(np.ascontiguousarray(np.stack(control_imgs)))
-    control = host.to(device, non_blocking=True).to(torch.float32).div_(255.0).clamp_(0, 1)
+    control = _upload_images(control_imgs, device).to(torch.float32).div_(255.0).clamp_(0, 1)
     control = control.permute(0, 3, 1, 2).contiguous()
     if not disable_preprocess_model:
         if preprocess_model is None:

@@ -123,6 +123,84 @@ def test_upsample_conv_as_phase_convs(ctx, cfg, n, H, W, C):
                     assert (pw[2 * a + bb, :, t, u] - want).abs().max().item() <= 2e-3   # one bf16 rounding of |w| <~ 0.4
 
 
+@pytest.mark.parametrize("cfg", [64, 128, 2128, 2256])
+@pytest.mark.parametrize("n,Ho,Wo,C,Co", [(1, 32, 32, 128, 128), (2, 12, 20, 64, 128), (1, 20, 36, 256, 256), (1, 6, 10, 128, 256)])
+def test_conv3x3_stride2_implicit_gemm(ctx, cfg, n, Ho, Wo, C, Co):
+    """Downsample.forward (model.py:92-101): F.pad(x, (0,1,0,1)) + 3x3 stride-2 conv. The A tiles are gathered at pixel
+    stride 2 by the tensor map (elementStrides), the pad is the TMA unit's zero fill; partial tiles, batch 2."""
+    _lib, L, dev = ctx
+    g = torch.Generator().manual_seed(Ho + Wo + C + Co)
+    x = torch.randn(n, C, 2 * Ho, 2 * Wo, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Co, C, 3, 3, generator=g) * 0.03).to(dev).bfloat16()
+    b = torch.randn(Co, generator=g).to(dev)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), b, stride=2)
+    assert ref.shape == (n, Co, Ho, Wo)
+    act = x.permute(0, 2, 3, 1).contiguous()
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Co, 9 * C)
+    out = torch.full((n, Ho, Wo, Co), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_conv3x3_s2_bf16(act.data_ptr(), wk.data_ptr(), b.data_ptr(), n, Ho, Wo, C, Co, out.data_ptr(), cfg,
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    _close(out.permute(0, 3, 1, 2), ref, 1e-2)
+
+
+@pytest.mark.parametrize("cfg", [64, 128, 2128, 2256])
+@pytest.mark.parametrize("n,H,W,C,Co", [(1, 32, 32, 512, 512), (2, 24, 40, 32, 128), (1, 20, 36, 128, 256)])
+def test_conv1x1_on_the_conv_epilogue(ctx, cfg, n, H, W, C, Co):
+    """1x1 conv as a single-tap implicit GEMM (attention proj_out with its residual, the 32-channel tap gather of
+    Encoder.conv_in: C < 64 is zero-filled to one 64-channel chunk by the TMA unit)."""
+    _lib, L, dev = ctx
+    g = torch.Generator().manual_seed(H + W + C + Co)
+    x = torch.randn(n, C, H, W, generator=g).to(dev).bfloat16()
+    w = (torch.randn(Co, C, 1, 1, generator=g) * 0.05).to(dev).bfloat16()
+    b = torch.randn(Co, generator=g).to(dev)
+    resid = torch.randn(n, H, W, Co, generator=g).to(dev).bfloat16()
+    ref = F.conv2d(x.float(), w.float(), b) + resid.float().permute(0, 3, 1, 2)
+    act = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((n, H, W, Co), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_conv1x1_bf16(act.data_ptr(), w.view(Co, C).contiguous().data_ptr(), b.data_ptr(), n, H, W, C, Co,
+                                 out.data_ptr(), resid.data_ptr(), cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    _close(out.permute(0, 3, 1, 2), ref, 1e-2)
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("P,C", [(256, 128), (384, 512), (1000, 512), (240, 64)])
+def test_materialised_attention_in_three_gemm_passes(ctx, cfg, P, C):
+    """AttnBlock (model.py:181-205): softmax(q k^T C^-1/2) v as pass 1 (group maxima), pass 2 (exp2 against the row shift,
+    bf16 probabilities + group sums) and pass 3 (P V scaled by 1 / sum); key counts that are not multiples of 64."""
+    _lib, L, dev = ctx
+    g = torch.Generator().manual_seed(P + C + cfg)
+    q = torch.randn(P, C, generator=g).to(dev).bfloat16()
+    k = torch.randn(P, C, generator=g).to(dev).bfloat16()
+    v = torch.randn(P, C, generator=g).to(dev).bfloat16()
+    s = q.float() @ k.float().t()
+    ng = (P + 63) // 64
+    part = torch.full((ng, P), float("nan"), device=dev)
+    _lib.check(L.ir_gemm_attn_pass(q.data_ptr(), k.data_ptr(), P, P, C, C, C, 1, 1.0, None, part.data_ptr(), None, 0, cfg,
+                                   _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    sp = F.pad(s, (0, ng * 64 - P), value=float("-inf")).view(P, ng, 64)
+    _close(part.t(), sp.amax(dim=2), 1e-3)
+    alpha2 = C ** -0.5 * 1.4426950408889634
+    shift = (part.amax(dim=0) * alpha2).contiguous()
+    pm = torch.full((P, P), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_gemm_attn_pass(q.data_ptr(), k.data_ptr(), P, P, C, C, C, 2, alpha2, shift.data_ptr(), part.data_ptr(),
+                                   pm.data_ptr(), P, cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    e = torch.exp2(s * alpha2 - shift[:, None])
+    _close(pm, e, 1e-2)
+    _close(part.t(), F.pad(e, (0, ng * 64 - P)).view(P, ng, 64).sum(dim=2), 2e-3)
+    inv_l = (1.0 / part.sum(dim=0)).contiguous()
+    vt = v.t().contiguous()
+    out = torch.full((P, C), float("nan"), device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_gemm_attn_pass(pm.data_ptr(), vt.data_ptr(), P, C, P, P, P, 3, 1.0, inv_l.data_ptr(), None,
+                                   out.data_ptr(), C, cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.softmax(s * C ** -0.5, dim=1) @ v.float()
+    _close(out, ref, 1.5e-2)
+
+
 @pytest.mark.parametrize("B,T", [(1, 256), (2, 1000), (1, 4096), (3, 1296), (1, 72)])
 def test_qkv_heads_and_tcgen05_attention(ctx, B, T):
     _lib, L, dev = ctx
