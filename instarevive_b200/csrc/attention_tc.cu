@@ -15,6 +15,9 @@
 //               running max grew by more than 2^8), exp2 with packed FFMA2 / FADD2 row math (optionally a compile-time
 //               share of the exponentials on the FMA pipe: Cody-Waite split + degree-3 minimax polynomial, relative
 //               error 7.5e-5, far below the bf16 rounding of P), tcgen05.st of the bf16 P row.
+// The softmax denominator is accumulated by the tensor core: shared-memory row 72 of every V^T tile is a row of ones (one
+// of the 8 padding rows of the N = 80 P V MMA; the TMA box covers the 72 real rows only), so O[:, 72] = sum_k P[:, k] in
+// fp32, rescaled with O and consistent with the bf16 P the numerator sees (sharp-softmax error 0.025 -> 0.016).
 // setmaxnreg moves registers from warps 0-3 to the softmax warps (S row = 128 live registers).
 // head_dim 72 is handled without padding the data in HBM: q / k are stored head-major [B][H][T][72] and v transposed
 // [B][H][72][Tp] by the qkv GEMM epilogue (EPI_QKV); TMA boxes read 64 + 16 columns and the tensor-map bounds make the
@@ -120,7 +123,11 @@ IR_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, u
 // ORDER > 0: the exponential sections of the two query tiles take turns (token passing through two mbarriers): one
 // tile's MUFU section runs against the other tile's TMEM load / row max / MMAs. The token is handed over after ORDER
 // of the 4 column chunks of the row (4 = strictly exclusive sections).
-template <int EMU8, int ORDER, bool TRACE = false>
+// TCSUM: the softmax denominator comes out of the tensor core: row 72 of every V^T tile in shared memory is a row of ones
+// (rows 72..79 are the padding of the N = 80 MMA; the TMA box covers only the 72 real rows, the padding rows are written
+// once per CTA), so O[:, 72] = sum_k P[:, k] accumulates in fp32 beside the output, is rescaled with it, and the softmax
+// threads no longer add up their exponentials (64 packed adds per row and tile off the issue-bound exponential section).
+template <int EMU8, int ORDER, bool TRACE = false, bool TCSUM = true>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant__ CUtensorMap tmK16,
                const __grid_constant__ CUtensorMap tmVT, const AttnTcDev p) {
@@ -179,6 +186,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (TCSUM) {
+    // rows 72..79 of the 2 * STAGES V^T atoms ([80 rows][64 keys] bf16, 128 B per row): row 72 = ones, the rest zeros.
+    // Whole rows of one value, so the 128 B swizzle does not matter. 8 rows x 8 16-byte chunks per atom.
+    for (int i = threadIdx.x; i < 2 * STAGES * 64; i += NTHREADS) {
+      const int atom = i >> 6, r = (i >> 3) & 7, c = i & 7;
+      uint8_t* base = sKV + (atom >> 1) * STAGE_BYTES + K64_BYTES + K16_BYTES + (atom & 1) * VT_ATOM_BYTES;
+      const uint32_t w = r == 0 ? 0x3F803F80u : 0u;
+      *reinterpret_cast<uint4*>(base + (HD + r) * 128 + c * 16) = make_uint4(w, w, w, w);
+    }
+    fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async-proxy) operand reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,7 +232,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
           mbar_wait(&v_empty[vs], vp ^ 1);
           uint8_t* st = sKV + vs * STAGE_BYTES + K64_BYTES + K16_BYTES;
           if (leader) {
-            mbar_arrive_expect_tx(&v_full[vs], 2 * VT_ATOM_BYTES);
+            mbar_arrive_expect_tx(&v_full[vs], 2 * (TCSUM ? HD * 128 : VT_ATOM_BYTES));
             tma_load_4d(st, &tmVT, &v_full[vs], jv * BKV, 0, head, b);
             tma_load_4d(st + VT_ATOM_BYTES, &tmVT, &v_full[vs], jv * BKV + 64, 0, head, b);
           }
@@ -364,7 +382,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
         const float alpha = grow ? fast_exp2(m_used - m_new) : 1.0f;
         if (grow) m_used = m_new;
         const uint64_t alpha2 = pack2(alpha, alpha);
-        l2 = fma2(l2, alpha2, pack2(0.f, 0.f));
+        if (!TCSUM) l2 = fma2(l2, alpha2, pack2(0.f, 0.f));
         if (j > 0) {
           // O_qt holds P V(0..j-1): complete, because S(j) (observed through s_full) was issued behind P V(j-1)
 #pragma unroll
@@ -408,17 +426,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
               e0 = fast_exp2(x0);
               e1 = fast_exp2(x1);
             }
-            if (pr & 1)
-              sum_b = add2(sum_b, pack2(e0, e1));
-            else
-              sum_a = add2(sum_a, pack2(e0, e1));
+            if (!TCSUM) {
+              if (pr & 1)
+                sum_b = add2(sum_b, pack2(e0, e1));
+              else
+                sum_a = add2(sum_a, pack2(e0, e1));
+            }
             pk[g * 4 + pr] = pack_bf16x2(e0, e1);
           }
         }
         tmem_st_32x16(t_s + c * 16, pk);
         if (ORDER > 0 && c == ORDER - 1) mbar_arrive(&order[qt ^ 1]);   // hand the MUFU over
       }
-      l2 = add2(l2, add2(sum_a, sum_b));
+      if (!TCSUM) l2 = add2(l2, add2(sum_a, sum_b));
       if (quarter == 0) stamp(qt, j, 5);
       tmem_st_wait();        // P (and a rescaled O) are in TMEM
       tc_fence_before();
@@ -427,10 +447,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
     }
     float l_lo, l_hi;
     unpack2(l2, l_lo, l_hi);
-    const float l = l_lo + l_hi;
+    float l = l_lo + l_hi;
     // ---- epilogue: O / l -> bf16 -> out[(b*T + row)][head*72 + d]
     mbar_wait(&o_full[qt], 0);
     tc_fence_after();
+    uint32_t o2[16];   // accumulator columns 64..79: d = 64..71, then (TCSUM) the row sum in column 72
+    tmem_ld_32x16(t_o + 64, o2);
+    tmem_ld_wait();
+    if (TCSUM) l = __uint_as_float(o2[8]);
     const float inv = l > 0.f ? 1.0f / l : 0.f;
     uint32_t o[32];
     bf16* og = p.out + ((long)b * p.T + row) * p.ldo + head * HD;
@@ -449,15 +473,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant_
         }
       }
     }
-    uint32_t o2[16];
-    tmem_ld_32x16(t_o + 64, o2);
-    tmem_ld_wait();
     if (row < p.T) {
       uint4 u = make_uint4(pack_bf16x2(__uint_as_float(o2[0]) * inv, __uint_as_float(o2[1]) * inv),
                            pack_bf16x2(__uint_as_float(o2[2]) * inv, __uint_as_float(o2[3]) * inv),
                            pack_bf16x2(__uint_as_float(o2[4]) * inv, __uint_as_float(o2[5]) * inv),
                            pack_bf16x2(__uint_as_float(o2[6]) * inv, __uint_as_float(o2[7]) * inv));
-      *reinterpret_cast<uint4*>(og + 64) = u;   // columns 64..71; accumulator columns 72..79 are padding
+      *reinterpret_cast<uint4*>(og + 64) = u;   // columns 64..71; accumulator columns 72..79 are the row sum / padding
     }
   }
 
@@ -478,6 +499,10 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.head_dim == HD, "attention_tc: head_dim %d unsupported (kernel is specialised for %d)", a.head_dim, HD);
   IR_REQUIRE(a.q && a.k && a.vt && a.out && a.B > 0 && a.H > 0 && a.T > 0, "attention_tc: bad arguments");
   IR_REQUIRE(a.Tp % 8 == 0 && a.Tp >= a.T && a.ldo % 8 == 0, "attention_tc: Tp must be a multiple of 8 and >= T");
+  static const bool tcsum = [] {
+    const char* e = debug_env("IR_ATTN_TCSUM");   // A/B switch of debug builds: 0 = row sums on the CUDA cores
+    return !(e && e[0] == '0');
+  }();
   CUtensorMap mk64, mk16, mvt;
   {
     const uint64_t dims[4] = {(uint64_t)HD, (uint64_t)a.T, (uint64_t)a.H, (uint64_t)a.B};
@@ -490,7 +515,8 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   {
     const uint64_t dims[4] = {(uint64_t)a.T, (uint64_t)HD, (uint64_t)a.H, (uint64_t)a.B};
     const uint64_t strides[3] = {(uint64_t)a.Tp * 2, (uint64_t)HD * a.Tp * 2, (uint64_t)a.H * HD * a.Tp * 2};
-    const uint32_t box[4] = {64, NV, 1, 1};
+    // TCSUM kernels: the box covers the 72 real rows; rows 72..79 of the shared-memory atoms hold the ones row / zeros
+    const uint32_t box[4] = {64, (uint32_t)(tcsum ? HD : NV), 1, 1};
     IR_TRY(make_tensor_map(&mvt, a.vt, 4, dims, strides, box, 128));
   }
   AttnTcDev p;
@@ -503,11 +529,13 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
   p.inv_scale_log2e = 1.0f / p.scale_log2e;
   p.trace = g_attn_trace;
   dim3 grid((a.T + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-  // share of the exponentials evaluated on the FMA pipe: EMU8 of every 8 key pairs. 2 (25 %) balances the MUFU and
-  // issue-slot budgets of the softmax warps; IR_ATTN_EMU overrides it for measurements (tools/gpu_attn_probe.py).
+  // share of the exponentials evaluated on the FMA pipe: EMU8 of every 8 key pairs. With the row sums on the tensor core
+  // (TCSUM) 3 of 8 balances the MUFU and issue-slot budgets of the softmax warps (B8 T4096: 673 us against 699 / 701 us at
+  // 2 / 4 of 8; 678 us for the old kernel with register row sums at its own optimum of 2); IR_ATTN_EMU overrides it for
+  // measurements (tools/gpu_attn_probe.py, tools/gpu_attn_sweep.sh).
   static const int emu = [] {
     const char* e = debug_env("IR_ATTN_EMU");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 3;
     return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();
   auto launch = [&](auto kernel) -> int {
@@ -523,10 +551,16 @@ int attention_tc_launch(const AttnTcArgs& a, cudaStream_t stream) {
     const int v = e ? atoi(e) : 3;
     return v < 0 ? 0 : (v > 4 ? 4 : v);
   }();
+  if (!tcsum) {
+    IR_TRY(launch(attn_tc_kernel<2, 3, false, false>));
+    IR_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return IR_OK;
+  }
   if (g_attn_trace) {
     switch (order) {
       case 0: return launch(attn_tc_kernel<2, 0, true>);
-      case 3: return launch(attn_tc_kernel<2, 3, true>);
+      case 3: return launch(attn_tc_kernel<3, 3, true>);
       default: return launch(attn_tc_kernel<2, 4, true>);
     }
   }

@@ -102,6 +102,8 @@ struct GemmDev {
   int att_mode;
   const float* att_row;
   float* att_out;
+  int red_add;        // EPI_F32 row-owner epilogue, in-place update without a bf16 copy: x += gate * (acc + bias) leaves as a
+                      // TMA reduce-add store (the residual is never read by the SM)
   int row_path;       // linear GEMM: row-owner epilogue with TMA-store boxes (host-checked alignment), else the transposing one
   long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
 };
@@ -139,6 +141,13 @@ IR_DEVINL void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, 
 }
 IR_DEVINL void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// TMA reduce-store: global[box] += shared[box] (fp32 add performed in L2; every element is touched once per launch)
+IR_DEVINL void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
@@ -639,7 +648,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t rowf0 = smem_u32(wbase) + (uint32_t)lane * 128u, rowf1 = rowf0 + 4096u;
         int nbox = 0;   // bf16 outputs: boxes alternate
         uint64_t* rb = &r_bar[warp - 4];
-        const bool has_resid = F32 && p.resid_f32 != nullptr;
+        const bool red_add = F32 && p.red_add;
+        const bool has_resid = F32 && p.resid_f32 != nullptr && !red_add;
         const bool want_bf16 = !F32 || p.out_bf16 != nullptr;
         constexpr int PAIRS = BN / 64;
         uint32_t rphase = 0;
@@ -811,7 +821,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_proxy_async();   // generic-proxy writes of the boxes -> async-proxy (TMA) reads
             __syncwarp();
             if (lane == 0 && rows_any && !(EPI == EPI_ATTN && p.att_mode == 1)) {
-              if (F32) {
+              if (F32 && red_add) {
+                tma_reduce_add_3d(&tmF, wbase, col0, row0, b);
+                if (col0 + 32 < p.N) tma_reduce_add_3d(&tmF, wbase + 4096, col0 + 32, row0, b);
+              } else if (F32) {
                 tma_store_3d(&tmF, wbase, col0, row0, b);
                 if (col0 + 32 < p.N) tma_store_3d(&tmF, wbase + 4096, col0 + 32, row0, b);
               }
@@ -1228,6 +1241,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 
 static int num_sms() { return device_num_sms(); }
 
+static constexpr int RED_ADD_DEFAULT = 0;   // measured on B200 (interleaved A/B, 1024^2 step): cross-proj / after_proj 23.2 -> 22.8 us, fc2 47.1 -> 47.4 us, step 21.6 vs 21.5-21.8 ms: a wash -> off
 static constexpr int ROW_PATH_DEFAULT = 1;   // measured on B200: plain bf16 gains (qkv-like 29.3 -> 27.4 us), GELU and fp32-residual lose (34.9 -> 40.8, 18.1 -> 22.6 us)
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_slots = 1, g_gemm_trace_next = 0;
@@ -1563,6 +1577,17 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       }();
       const int bit = a.epi == EPI_BF16 ? 1 : (a.epi == EPI_BF16_GELU ? 2 : 4);
       p.row_path = (row_mask & bit) ? 1 : 0;
+      // in-place residual update with no bf16 copy (cross-attention proj, fc2, after_proj: PixArtMS.py:76-79,
+      // pixart_controlnet.py:240): row-owner epilogue whose boxes leave by TMA reduce-add (IR_GEMM_REDADD=0: A/B switch
+      // of debug builds)
+      static const int red_on = [] {
+        const char* e = debug_env("IR_GEMM_REDADD");
+        return e ? atoi(e) : RED_ADD_DEFAULT;
+      }();
+      if (f32 && red_on && a.resid_f32 && a.resid_f32 == a.out_f32 && !a.out_bf16) {
+        p.row_path = 1;
+        p.red_add = 1;
+      }
       if (a.epi == EPI_ATTN) p.row_path = 1;   // the only epilogue that implements it
     }
   }

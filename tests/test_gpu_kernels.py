@@ -61,6 +61,16 @@ def test_gemm_f32_gate_residual_inplace_and_batched(ctx, cfg):
     torch.cuda.synchronize()
     _close(x, ref, 2e-3)       # in place: out aliases the residual
     _close(xb, ref, 1e-2)      # bf16 copy
+    # in place without a bf16 copy (cross-attention proj / fc2 / after_proj): the update leaves as a TMA reduce-add; an M
+    # tail (700 rows) and no gate as well
+    for rows, gt in ((M, gate), (700, None)):
+        x2 = torch.randn(rows, N, generator=g).to(dev)
+        ref2 = x2 + (gt[:, 2 * N:3 * N].repeat_interleave(T, 0)[:rows] if gt is not None else 1.0) * (A[:rows].float() @ W.float().t() + bias)
+        _lib.check(L.ir_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), rows, N, K, 1, 0, 0, 0, 2, 1.0, None, x2.data_ptr(),
+                                  x2.data_ptr(), (gt.data_ptr() + 2 * N * 4) if gt is not None else None, 6 * N, T, cfg,
+                                  _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        _close(x2, ref2, 2e-3)
     # batched with a shared A operand and per-batch bias (the caption K/V projection of all blocks in one launch)
     nb, Mb = 5, 77
     A2 = (torch.randn(Mb, K, generator=g) * 0.5).to(dev).bfloat16()
