@@ -298,6 +298,8 @@ def run_cuda(args):
         net.set_dual_chain(False)
     # encoder + decoder on this repo's own kernels: nothing from cuDNN / ATen convolutions runs in any timed region
     vae = ir.AutoencoderKL(weights.make_vae_state_dict(dec_seed=2, enc_seed=5), device=dev)
+    if args.plain_schedule:
+        vae.set_cuda_graphs(False)
     sched = ir.DDPMSchedulerLite()
     _, _, y, mask, _ = weights.make_inputs(1, 8, 8, seed=9, lens=(77,))
     y, mask = y.to(dev), mask.to(dev)

@@ -139,6 +139,10 @@ int ir_vae_num_params(const ir_vae* h);
 int ir_vae_param_info(const ir_vae* h, int i, char* name, int name_cap, long long* numel);
 int ir_vae_load_param(ir_vae* h, const char* name, const float* src_dev, long long numel, void* stream);
 size_t ir_vae_workspace_bytes(const ir_vae* h, int B, int h_lat, int w_lat);
+/* CUDA-graph replay of ir_vae_decode / ir_vae_encode (default on): the second call with a given (batch, size, workspace,
+ * output affine) captures the ~110 launches of the call, later calls replay them (input / output staged through fixed
+ * buffers of the workspace). enable = 0: plain stream-ordered launches, cached graphs dropped. */
+int ir_vae_set_graphs(ir_vae* h, int enable);
 /* out (B,3,8h,8w) fp32 = decode(z * in_scale) * out_scale + out_shift; z: (B,4,h,w) fp32 latents.
  * in_scale = 1/scaling_factor and out = x/2 + 0.5 reproduce test_scripts/inference.py:116-117,140-142. */
 int ir_vae_decode(ir_vae* h, const float* z, float* out, int B, int h_lat, int w_lat, float in_scale, float out_scale,

@@ -43,6 +43,7 @@ PROTOTYPES = {
     "ir_dit_reserve": (_i, [_vp, _i, _i]),
     "ir_dit_set_graphs": (_i, [_vp, _i]),
     "ir_dit_set_dual_chain": (_i, [_vp, _i]),
+    "ir_vae_set_graphs": (_i, [_vp, _i]),
     "ir_dit_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp, _sz, _vp]),
     "ir_dit_patch_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ir_eps_to_x0": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),

@@ -341,6 +341,15 @@ int ir_vae_load_param(ir_vae* h, const char* name, const float* src_dev, long lo
   return vae_load_param(h->v, name, src_dev, (long)numel, (cudaStream_t)stream);
 }
 
+int ir_vae_set_graphs(ir_vae* h, int enable) {
+  if (!h) {
+    set_last_error("ir_vae_set_graphs: null handle");
+    return IR_ERR_INVALID;
+  }
+  vae_set_graphs(h->v, enable != 0);
+  return IR_OK;
+}
+
 size_t ir_vae_workspace_bytes(const ir_vae* h, int B, int h_lat, int w_lat) {
   return h ? vae_workspace_bytes(h->v, B, h_lat, w_lat) : 0;
 }

@@ -685,8 +685,11 @@ int vae_create(const VaeConfig& cfg, Vae** out) {
   return IR_OK;
 }
 
+void vae_release_graphs(Vae* v);
+
 void vae_destroy(Vae* v) {
   if (!v) return;
+  vae_release_graphs(v);
   cudaFree(v->wb);
   cudaFree(v->wf);
   cudaFree(v->co_w);
@@ -829,6 +832,7 @@ struct VaeWs {
   unsigned* fin_count = nullptr;   // [B] tickets (zeroed at the start of every decode / encode call)
   bf16* im2col = nullptr;   // encoder only: A operand of conv_in ([B*H*W][32]: 27 taps of the 3-channel image + 5 zeros)
   float* f32tmp = nullptr;  // encoder only: fp32 NHWC output of conv_out
+  float *g_in = nullptr, *g_out = nullptr;   // CUDA-graph replay: the call's input / output staged at fixed addresses
 };
 
 static const int GN_MAX_CHUNKS = 2048;
@@ -872,6 +876,8 @@ static size_t vae_carve(const Vae* v, VaeWs& w, void* base, int B, int h, int wd
   w.stats = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * sizeof(float)));
   w.fin_scratch = reinterpret_cast<double*>(take((size_t)B * GN_FIN_BLOCKS * 64 * sizeof(double)));
   w.fin_count = reinterpret_cast<unsigned*>(take((size_t)B * sizeof(unsigned)));
+  w.g_in = reinterpret_cast<float*>(take((size_t)B * v->cfg.z_channels * h * wd * sizeof(float)));
+  w.g_out = reinterpret_cast<float*>(take((size_t)B * v->cfg.out_ch * 64 * h * wd * sizeof(float)));
   return (off + 255) & ~size_t(255);
 }
 
@@ -1107,8 +1113,8 @@ static int attn_block(VCtx& c, const std::string& name, int& cur, int H, int W, 
   return IR_OK;
 }
 
-int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
-               float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+static int vae_decode_body(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
+                           float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   IR_REQUIRE(z && out && B > 0 && h > 0 && w > 0, "vae_decode: bad arguments");
   IR_REQUIRE(h % 2 == 0 && w % 2 == 0, "vae_decode: latent size must be even");
   for (int i = 0; i < (int)v->params.size() && (v->first_encoder_param < 0 || i < v->first_encoder_param); ++i)
@@ -1255,6 +1261,8 @@ static size_t vae_enc_carve(const Vae* v, VaeWs& w, void* base, int B, int H, in
   w.fin_scratch = reinterpret_cast<double*>(take((size_t)B * GN_FIN_BLOCKS * 64 * sizeof(double)));
   w.fin_count = reinterpret_cast<unsigned*>(take((size_t)B * sizeof(unsigned)));
   w.f32tmp = reinterpret_cast<float*>(take((size_t)B * P * 2 * v->cfg.z_channels * sizeof(float)));
+  w.g_in = reinterpret_cast<float*>(take((size_t)B * 3 * H * W * sizeof(float)));
+  w.g_out = reinterpret_cast<float*>(take((size_t)B * P * 2 * v->cfg.z_channels * sizeof(float)));
   return (off + 255) & ~size_t(255);
 }
 
@@ -1298,8 +1306,8 @@ static int downsample(VCtx& c, const std::string& name, const bf16* x, bf16* y, 
 
 // AutoencoderKL.encode up to the moments (autoencoder.py:82-86): Encoder.forward (model.py:521-546) + quant_conv.
 // x: (B,3,H,W) fp32 in [-1,1]; moments: (B, 2z, H/8, W/8) fp32 (mean | logvar).
-int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
-               cudaStream_t s) {
+static int vae_encode_body(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                           cudaStream_t s) {
   IR_REQUIRE(v->cfg.with_encoder && v->first_encoder_param >= 0, "vae_encode: handle was created without the encoder");
   IR_REQUIRE(x && moments && B > 0 && H > 0 && W > 0, "vae_encode: bad arguments");
   IR_REQUIRE(H % 16 == 0 && W % 16 == 0, "vae_encode: image size must be a multiple of 16 (got %dx%d)", H, W);
@@ -1376,6 +1384,134 @@ int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void
   IR_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return IR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA-graph replay
+// A decode / encode call is 100-120 launches whose sizes, order and device pointers are fixed for a given (shape, workspace,
+// output affine): the second call with a key captures the body into a graph (on a stream of the library's own: the
+// caller's may be the legacy default stream), later calls copy the input to a fixed staging buffer of the workspace, launch
+// the graph and copy the result back. Same kernels in the same order: bit-identical to the eager path (the first call with
+// a key, the per-launch profile pass and calls made while the caller's stream is itself being captured stay eager).
+static bool vae_stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+static void vae_destroy_graphs(Vae* v) {
+  for (VaeGraph& g : v->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  v->graphs.clear();
+}
+
+void vae_set_graphs(Vae* v, bool on) {
+  v->graphs_enabled = on;
+  if (!on) vae_destroy_graphs(v);
+}
+
+void vae_release_graphs(Vae* v) {
+  vae_destroy_graphs(v);
+  if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
+  v->cap_stream = nullptr;
+}
+
+// body(in, out, stream) runs the eager path on the given pointers
+template <typename Body>
+static int vae_run_graphed(Vae* v, const VaeGraph& key, const float* in, size_t in_bytes, float* out, size_t out_bytes,
+                           float* g_in, float* g_out, cudaStream_t s, Body body) {
+  const bool use_graph = v->graphs_enabled && !prof_enabled() && !vae_stream_is_capturing(s);
+  if (!use_graph) return body(in, out, s);
+  VaeGraph* hit = nullptr;
+  for (VaeGraph& g : v->graphs)
+    if (g.same_key(key)) hit = &g;
+  if (!hit) {
+    // first call with this key: eager (one-time initialisation -- shared-memory opt-ins, the driver entry point -- stays
+    // outside any capture)
+    if (v->graphs.size() >= 16) vae_destroy_graphs(v);
+    v->graphs.push_back(key);
+    return body(in, out, s);
+  }
+  IR_CUDA_CHECK(cudaMemcpyAsync(g_in, in, in_bytes, cudaMemcpyDeviceToDevice, s));
+  if (!hit->exec) {
+    const long long before = launch_count_value();
+    if (!v->cap_stream) IR_CUDA_CHECK(cudaStreamCreateWithFlags(&v->cap_stream, cudaStreamNonBlocking));
+    if (cudaStreamBeginCapture(v->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      vae_set_graphs(v, false);
+      return body(in, out, s);
+    }
+    const int st = body(g_in, g_out, v->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(v->cap_stream, &graph);
+    if (st != IR_OK || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (st == IR_OK) set_last_error("vae: graph capture failed: %s", cudaGetErrorString(ce));
+      vae_set_graphs(v, false);   // not again on this handle; the eager path serves the call
+      return st != IR_OK ? st : body(in, out, s);
+    }
+    const int launches = (int)(launch_count_value() - before);
+    count_launch(-launches);   // nothing ran during capture; replays are counted below
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      cudaGetLastError();
+      vae_set_graphs(v, false);
+      return body(in, out, s);
+    }
+    // `hit` may have been invalidated by nothing: the vector is not touched between the lookup and here
+    hit->exec = exec;
+    hit->launches = launches;
+  }
+  IR_CUDA_CHECK(cudaGraphLaunch(hit->exec, s));
+  count_launch(hit->launches);
+  IR_CUDA_CHECK(cudaMemcpyAsync(out, g_out, out_bytes, cudaMemcpyDeviceToDevice, s));
+  return IR_OK;
+}
+
+int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,
+               float out_shift, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  IR_REQUIRE(z && out && B > 0 && h > 0 && w > 0, "vae_decode: bad arguments");
+  const size_t need = vae_workspace_bytes(v, B, h, w);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("vae_decode: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  VaeWs ws;
+  vae_carve(v, ws, workspace, B, h, w);
+  VaeGraph key;
+  key.kind = 0; key.B = B; key.H = h; key.W = w; key.ws = workspace;
+  key.f[0] = in_scale; key.f[1] = out_scale; key.f[2] = out_shift;
+  return vae_run_graphed(v, key, z, (size_t)B * v->cfg.z_channels * h * w * sizeof(float), out,
+                         (size_t)B * v->cfg.out_ch * 64 * h * w * sizeof(float), ws.g_in, ws.g_out, s,
+                         [&](const float* in, float* o, cudaStream_t st) {
+                           return vae_decode_body(v, in, o, B, h, w, in_scale, out_scale, out_shift, workspace, workspace_bytes, st);
+                         });
+}
+
+int vae_encode(Vae* v, const float* x, float* moments, int B, int H, int W, void* workspace, size_t workspace_bytes,
+               cudaStream_t s) {
+  IR_REQUIRE(v->cfg.with_encoder && v->first_encoder_param >= 0, "vae_encode: handle was created without the encoder");
+  IR_REQUIRE(x && moments && B > 0 && H > 0 && W > 0, "vae_encode: bad arguments");
+  IR_REQUIRE(H % 16 == 0 && W % 16 == 0, "vae_encode: image size must be a multiple of 16 (got %dx%d)", H, W);
+  const size_t need = vae_encode_workspace_bytes(v, B, H, W);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("vae_encode: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return IR_ERR_WORKSPACE;
+  }
+  VaeWs ws;
+  vae_enc_carve(v, ws, workspace, B, H, W);
+  VaeGraph key;
+  key.kind = 1; key.B = B; key.H = H; key.W = W; key.ws = workspace;
+  return vae_run_graphed(v, key, x, (size_t)B * 3 * H * W * sizeof(float), moments,
+                         (size_t)B * 2 * v->cfg.z_channels * (H / 8) * (W / 8) * sizeof(float), ws.g_in, ws.g_out, s,
+                         [&](const float* in, float* o, cudaStream_t st) {
+                           return vae_encode_body(v, in, o, B, H, W, workspace, workspace_bytes, st);
+                         });
 }
 
 }  // namespace ir

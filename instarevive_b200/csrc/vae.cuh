@@ -29,8 +29,23 @@ struct VaeParam {
   bool loaded = false;
 };
 
+// one cached CUDA graph of a decode (kind 0) / encode (kind 1) call; exec == nullptr: the key was seen once (eager run)
+struct VaeGraph {
+  int kind = 0, B = 0, H = 0, W = 0;
+  const void* ws = nullptr;
+  float f[3] = {0.f, 0.f, 0.f};   // decode: in_scale, out_scale, out_shift (baked into the captured kernels' arguments)
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+  bool same_key(const VaeGraph& o) const {
+    return kind == o.kind && B == o.B && H == o.H && W == o.W && ws == o.ws && f[0] == o.f[0] && f[1] == o.f[1] && f[2] == o.f[2];
+  }
+};
+
 struct Vae {
   VaeConfig cfg;
+  std::vector<VaeGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  bool graphs_enabled = true;
   std::vector<VaeParam> params;
   std::unordered_map<std::string, int> index;
   bf16* wb = nullptr;
@@ -49,6 +64,7 @@ struct Vae {
 int vae_create(const VaeConfig& cfg, Vae** out);
 void vae_destroy(Vae* v);
 int vae_load_param(Vae* v, const char* name, const float* src_dev, long numel, cudaStream_t s);
+void vae_set_graphs(Vae* v, bool on);   // CUDA-graph replay of decode / encode calls (default on)
 size_t vae_workspace_bytes(const Vae* v, int B, int h, int w);
 // z: (B,4,h,w) fp32 -> out: (B,3,8h,8w) fp32 = decode(z * in_scale) * out_scale + out_shift
 int vae_decode(Vae* v, const float* z, float* out, int B, int h, int w, float in_scale, float out_scale,

@@ -88,6 +88,11 @@ class AutoencoderKLDecoder:
             pass
 
     @torch.no_grad()
+    def set_cuda_graphs(self, enable: bool) -> None:
+        """CUDA-graph replay of decode / encode calls (default on: from the third call with a given batch / size the ~110
+        launches of a call are replayed as one graph). Off = plain stream-ordered launches."""
+        _lib.check(_lib.lib().ir_vae_set_graphs(self._handle, 1 if enable else 0), "ir_vae_set_graphs")
+
     def decode_tensor(self, z: torch.Tensor, in_scale: float = 1.0, out_scale: float = 1.0, out_shift: float = 0.0):
         """(B,4,h,w) latents -> (B,3,8h,8w) fp32 image = Decoder(post_quant_conv(z*in_scale))*out_scale + out_shift."""
         if z.device.type != "cuda":

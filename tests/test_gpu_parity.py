@@ -226,6 +226,41 @@ def test_vae_encode_matches_reference_golden(vae_full, golden_dir, tag):
     assert img.shape == (B, 3, H, W) and torch.isfinite(img).all()
 
 
+def test_vae_cuda_graph_replay_is_bit_identical_to_eager_launches(vae_full):
+    """ir_vae_decode / ir_vae_encode replay their ~110 launches as a CUDA graph from the third call with a key (first
+    eager, second captured + launched): identical inputs must give bit-identical outputs on every path, with fresh
+    caller tensors each call, a second shape in between and a different output affine (its own graph)."""
+    dev = _cuda()
+    g = torch.Generator().manual_seed(11)
+    z1, z2 = torch.randn(2, 4, 24, 32, generator=g), torch.randn(2, 4, 24, 32, generator=g)
+    zs = torch.randn(1, 4, 16, 16, generator=g)
+    x1 = torch.rand(1, 3, 96, 128, generator=g) * 2 - 1
+
+    def dec(z, **kw):
+        return vae_full.decode_tensor(z.to(dev), **kw).clone()   # a fresh device tensor every call
+
+    def enc(x):
+        return vae_full.encode_moments(x.to(dev)).clone()
+
+    vae_full.set_cuda_graphs(False)
+    ref1, ref2, refs, refe = dec(z1), dec(z2), dec(zs), enc(x1)
+    refa = dec(z1, in_scale=1.0 / 0.18215, out_scale=0.5, out_shift=0.5)
+    vae_full.set_cuda_graphs(True)
+    try:
+        for _ in range(2):
+            assert torch.equal(dec(z1), ref1)       # eager, then capture + launch
+        assert torch.equal(dec(z2), ref2)           # replay, other input values
+        assert torch.equal(dec(zs), refs) and torch.equal(dec(zs), refs) and torch.equal(dec(zs), refs)   # a second key
+        assert torch.equal(dec(z1), ref1)           # back to the first graph
+        for _ in range(3):
+            assert torch.equal(dec(z1, in_scale=1.0 / 0.18215, out_scale=0.5, out_shift=0.5), refa)       # affine is part of the key
+        for _ in range(4):
+            assert torch.equal(enc(x1), refe)
+        assert torch.equal(dec(z2), ref2)
+    finally:
+        vae_full.set_cuda_graphs(True)
+
+
 def test_vae_encode_rejects_bad_input(vae_full):
     dev = _cuda()
     with pytest.raises(ValueError):
