@@ -59,7 +59,7 @@ struct GemmDev {
   int M, N, K;
   int k_blocks;    // K-blocks per tile
   int raster_n;    // tile order: 1 = N blocks fastest, 0 = M blocks fastest
-  int gelu_erf;    // EPI_BF16_GELU: 1 = exact erf GELU, 0 = tanh approximation
+  int gelu_erf;    // EPI_BF16_GELU: 1 = exact erf GELU (launched as the EPI_BF16_GELU_ERF instantiation), 0 = tanh approximation
   int m_blocks;    // 128-row M tiles per batch entry (per image for conv)
   int m_units;     // scheduling units per batch entry: m_blocks (CG 1) or ceil(m_blocks / 2) pairs (CG 2)
   int n_blocks;
@@ -129,6 +129,23 @@ IR_DEVINL float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 256-bit global accesses of the direct row-owner epilogue (sm_100: LDG / STG .256): one full 32-byte sector per thread.
+// asm volatile keeps them in program order among themselves (the fp32 output may alias the residual, which is only read
+// through ldg_v8); no memory clobber, so that the compiler may hoist the read-only bias / gate loads across the stores.
+IR_DEVINL void ldg_v8(const float* src, float* r) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(src));
+}
+IR_DEVINL void stg_v8(float* dst, const float (&x)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]),
+               "f"(x[3]), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]));
+}
+IR_DEVINL void stg_v8(bf16* dst, const uint32_t (&x)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(x[0]), "r"(x[1]), "r"(x[2]),
+               "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
 }
 
 // ---------------------------------------------------------------------------------------------- conv epilogue helpers
@@ -633,8 +650,220 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     } else {
     bool row_path_done = false;
+    if constexpr (!CONV && EPI != EPI_ATTN) {
+      if (p.row_path == 2) {
+        // -------- linear GEMMs, direct row-owner epilogue: a thread owns one output row (its TMEM lane) and walks its
+        // warp's 32-column chunks straight from TMEM to global memory -- no shared-memory staging at all. The transposing
+        // epilogue moves every fp32 element through shared memory twice (256 KB per 128 x 256 tile) while the mainloop
+        // already runs the 128 B/clk port at its limit, and exposes the TMEM / shared-memory latencies of each chunk with
+        // only two warps per scheduler to hide them. Here the next chunk's accumulator (bf16 outputs) or residual row
+        // (fp32-residual epilogue) is in flight while the current chunk is computed, and a thread writes whole 32-byte
+        // sectors of its own row (256-bit stores), so the L2 sees full-sector writes in 32 different lines per instruction.
+        // Host-checked: N % 32 == 0, 32-byte aligned rows.
+        row_path_done = true;
+        constexpr int NCH = (BN / 32 + CSTEP - 1) / CSTEP;   // chunks per warp and tile
+        const uint32_t lane_tmem = tmem_base + ((uint32_t)(q * 32) << 16);
+        int it = 0;
+        for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
+          const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+          const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
+          const int b = mb / p.m_units;
+          const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          const int row = m_blk * BM + q * 32 + lane;
+          const bool row_ok = row < p.M;
+          const int colw = n_blk * BN;   // first column of the tile
+          auto chunk_col = [&](int i) { return colw + (chalf + i * CSTEP) * 32; };
+          auto chunk_ok = [&](int i) { return chalf + i * CSTEP < BN / 32 && chunk_col(i) < p.N; };
+          auto release = [&]() {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+            }
+          };
+          auto tload = [&](uint32_t (&v)[32], int i) {
+            tmem_ld_32x32(lane_tmem + (uint32_t)(buf * BN + (chalf + i * CSTEP) * 32), v);
+          };
+          // the chunk's 32 bias values (every lane reads the same addresses: broadcast loads, L1-resident), requested before
+          // the wait for the accumulator chunk so that their latency is not exposed in front of the first FMA
+          auto bload = [&](float4 (&bs)[8], int i) {
+            const bool on = p.bias != nullptr && chunk_ok(i);
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + (long)b * p.stride_bias + chunk_col(i));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bs[j] = on ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          };
+          // alpha * acc + bias of one 8-column piece
+          auto lin8 = [&](const uint32_t (&v)[32], int j8, const float4 (&bs)[8], float (&x)[8]) {
+            const float4 b0 = bs[2 * j8], b1 = bs[2 * j8 + 1];
+            x[0] = fmaf(__uint_as_float(v[8 * j8]), p.alpha, b0.x);
+            x[1] = fmaf(__uint_as_float(v[8 * j8 + 1]), p.alpha, b0.y);
+            x[2] = fmaf(__uint_as_float(v[8 * j8 + 2]), p.alpha, b0.z);
+            x[3] = fmaf(__uint_as_float(v[8 * j8 + 3]), p.alpha, b0.w);
+            x[4] = fmaf(__uint_as_float(v[8 * j8 + 4]), p.alpha, b1.x);
+            x[5] = fmaf(__uint_as_float(v[8 * j8 + 5]), p.alpha, b1.y);
+            x[6] = fmaf(__uint_as_float(v[8 * j8 + 6]), p.alpha, b1.z);
+            x[7] = fmaf(__uint_as_float(v[8 * j8 + 7]), p.alpha, b1.w);
+          };
+
+          if constexpr (EPI == EPI_F32) {
+            // x += gate * (alpha * acc + bias) on the fp32 residual stream (PixArtMS.py:71-79), optional bf16 copy. The residual
+            // row piece of the NEXT chunk is requested before the current one is computed; the first one before the wait for
+            // the accumulator, so that its latency runs under the tile's own MMAs (every element is read and written by the
+            // same thread of the same tile: nothing these loads can see is still to be written).
+            const int gate_row = row_ok ? row / p.rows_per_gate : 0;
+            float ra[32], rb[32];
+            float4 bs[8];
+            auto rload = [&](float (&r)[32], int i) {
+              if (p.resid_f32 && row_ok && chunk_ok(i)) {
+                const float* src = p.resid_f32 + (long)b * p.stride_of + (long)row * p.ldo_f + chunk_col(i);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ldg_v8(src + 8 * j, &r[8 * j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0.f;
+              }
+            };
+            auto emit = [&](const uint32_t (&v)[32], const float (&r)[32], int i) {
+              if (!row_ok || !chunk_ok(i)) return;
+              const int colc = chunk_col(i);
+              const float* gp = p.gate ? p.gate + (long)gate_row * p.gate_ld + colc : nullptr;
+              float* of = p.out_f32 + (long)b * p.stride_of + (long)row * p.ldo_f + colc;
+              bf16* ob = p.out_bf16 ? p.out_bf16 + (long)b * p.stride_ob + (long)row * p.ldo_b + colc : nullptr;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                  const int j8 = 2 * h + jj;
+                  float x[8];
+                  lin8(v, j8, bs, x);
+                  if (gp) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp) + 2 * j8);
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 2 * j8 + 1);
+                    x[0] *= g0.x; x[1] *= g0.y; x[2] *= g0.z; x[3] *= g0.w;
+                    x[4] *= g1.x; x[5] *= g1.y; x[6] *= g1.z; x[7] *= g1.w;
+                  }
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) x[e] += r[8 * j8 + e];
+                  stg_v8(of + 8 * j8, x);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) pk[4 * jj + e] = pack_bf16x2(x[2 * e], x[2 * e + 1]);
+                }
+                if (ob) stg_v8(ob + 16 * h, pk);
+              }
+            };
+            rload(ra, 0);
+            mbar_wait(&tfull_bar[buf], use & 1);
+            tc_fence_after();
+            if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+            uint32_t v[32];
+#pragma unroll 1
+            for (int i = 0; i < NCH; i += 2) {
+              tload(v, i);
+              bload(bs, i);
+              tmem_ld_wait();
+              if (NCH > 1) rload(rb, i + 1); else release();
+              emit(v, ra, i);
+              if constexpr (NCH > 1) {
+                tload(v, i + 1);
+                bload(bs, i + 1);
+                tmem_ld_wait();
+                if (i + 2 < NCH) rload(ra, i + 2); else release();
+                emit(v, rb, i + 1);
+              }
+            }
+          } else {
+            const int qT = (EPI == EPI_QKV) ? p.qkv_T : 1;
+            const int bb = (EPI == EPI_QKV) ? row / qT : 0;
+            const int tt = (EPI == EPI_QKV) ? row - bb * qT : 0;
+            float4 bs[8];
+            auto emit = [&](const uint32_t (&v)[32], int i) {
+              if (!row_ok || !chunk_ok(i)) return;
+              const int colc = chunk_col(i);
+              if constexpr (EPI == EPI_QKV) {
+                // head-major scatter of the qkv projection (q, k: [b][head][t][hd]; v transposed: [b][head][hd][Tp]); H * hd is a
+                // multiple of 32, so a chunk is all-q, all-k or all-v (warp-uniform), and hd a multiple of 8, so an 8-column
+                // piece never straddles a head
+                const int D1 = p.qkv_H * p.qkv_hd;
+                const int which = colc / D1;
+                const int cl = colc - which * D1;
+                if (which == 2) {
+                  // lanes are consecutive tokens: every column is one 64-byte run of the transposed layout
+                  bf16* dst = p.vt_heads + ((long)bb * D1 + cl) * p.qkv_Tp + tt;
+#pragma unroll
+                  for (int j8 = 0; j8 < 4; ++j8) {
+                    float x[8];
+                    lin8(v, j8, bs, x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dst[(long)(8 * j8 + e) * p.qkv_Tp] = __float2bfloat16(x[e]);
+                  }
+                } else {
+                  bf16* base = which == 0 ? p.q_heads : p.k_heads;
+                  int head = cl / p.qkv_hd, d = cl - head * p.qkv_hd;
+#pragma unroll
+                  for (int j8 = 0; j8 < 4; ++j8) {
+                    float x[8];
+                    lin8(v, j8, bs, x);
+                    bf16* dst = base + (((long)bb * p.qkv_H + head) * p.qkv_T + tt) * p.qkv_hd + d;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                                                                pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                    d += 8;
+                    if (d >= p.qkv_hd) {
+                      d -= p.qkv_hd;
+                      ++head;
+                    }
+                  }
+                }
+              } else {
+                bf16* ob = p.out_bf16 + (long)b * p.stride_ob + (long)row * p.ldo_b + colc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int jj = 0; jj < 2; ++jj) {
+                    float x[8];
+                    lin8(v, 2 * h + jj, bs, x);
+                    if constexpr (EPI == EPI_BF16_GELU_ERF) {   // exact GELU (nn.GELU default: SwinIR's Mlp)
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) x[e] = 0.5f * x[e] * (1.0f + erff(x[e] * 0.70710678118654752f));
+                    } else if constexpr (EPI == EPI_BF16_GELU) {   // tanh approximation (PixArt's Mlp, approximate="tanh")
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) x[e] = gelu_tanh_fast(x[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[4 * jj + e] = pack_bf16x2(x[2 * e], x[2 * e + 1]);
+                  }
+                  stg_v8(ob + 16 * h, pk);
+                }
+              }
+            };
+            mbar_wait(&tfull_bar[buf], use & 1);
+            tc_fence_after();
+            if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+            uint32_t va[32], vb[32];
+            tload(va, 0);
+#pragma unroll 1
+            for (int i = 0; i < NCH; i += 2) {
+              bload(bs, i);
+              tmem_ld_wait();
+              if (NCH > 1) tload(vb, i + 1); else release();
+              emit(va, i);
+              if constexpr (NCH > 1) {
+                bload(bs, i + 1);
+                tmem_ld_wait();
+                if (i + 2 < NCH) tload(va, i + 2); else release();
+                emit(vb, i + 1);
+              }
+            }
+          }
+          if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));
+        }
+      }
+    }
     if constexpr (!CONV && EPI != EPI_QKV) {
-      if (p.row_path) {
+      if (p.row_path == 1) {
         // -------- linear GEMMs, row-owner epilogue: a thread owns one output row (its TMEM lane) and 32 consecutive columns
         // per chunk. bf16 outputs: two chunks fill one 128 B row of a [64 col][32 row] box in the TMA SWIZZLE_128B layout and
         // leave by ONE TMA store per box. fp32-residual epilogue (x += gate * (A W^T + b), PixArtMS.py:71-79): the residual
@@ -768,18 +997,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 b4 = (p.bias && cok) ? __ldg(reinterpret_cast<const float4*>(bp) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float x0 = __uint_as_float(v[4 * j]) * p.alpha + b4.x, x1 = __uint_as_float(v[4 * j + 1]) * p.alpha + b4.y;
                 float x2 = __uint_as_float(v[4 * j + 2]) * p.alpha + b4.z, x3 = __uint_as_float(v[4 * j + 3]) * p.alpha + b4.w;
-                if (EPI == EPI_BF16_GELU) {
-                  if (p.gelu_erf) {   // exact GELU (nn.GELU default: SwinIR's Mlp); warp-uniform branch
-                    x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));
-                    x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
-                    x2 = 0.5f * x2 * (1.0f + erff(x2 * 0.70710678118654752f));
-                    x3 = 0.5f * x3 * (1.0f + erff(x3 * 0.70710678118654752f));
-                  } else {            // tanh approximation (PixArt's Mlp, approximate="tanh")
-                    x0 = gelu_tanh_fast(x0);
-                    x1 = gelu_tanh_fast(x1);
-                    x2 = gelu_tanh_fast(x2);
-                    x3 = gelu_tanh_fast(x3);
-                  }
+                if constexpr (EPI == EPI_BF16_GELU_ERF) {   // exact GELU (nn.GELU default: SwinIR's Mlp)
+                  x0 = 0.5f * x0 * (1.0f + erff(x0 * 0.70710678118654752f));
+                  x1 = 0.5f * x1 * (1.0f + erff(x1 * 0.70710678118654752f));
+                  x2 = 0.5f * x2 * (1.0f + erff(x2 * 0.70710678118654752f));
+                  x3 = 0.5f * x3 * (1.0f + erff(x3 * 0.70710678118654752f));
+                } else if constexpr (EPI == EPI_BF16_GELU) {   // tanh approximation (PixArt's Mlp, approximate="tanh")
+                  x0 = gelu_tanh_fast(x0);
+                  x1 = gelu_tanh_fast(x1);
+                  x2 = gelu_tanh_fast(x2);
+                  x3 = gelu_tanh_fast(x3);
                 }
                 if (F32) {
                   if (p.gate) {
@@ -911,7 +1138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // (the fp32-residual epilogue already keeps gate, residual and next residual in registers: prefetching there spills)
       // Linear GEMMs only: measured on B200, fc1 (GELU) 39.5 -> 35.1 us; the conv instantiations (GroupNorm partials, fewer
       // epilogue warps) lost ~3 % with it and keep the plain order.
-      constexpr bool PREFETCH_ACC = !CONV && (EPI == EPI_BF16 || EPI == EPI_BF16_GELU);
+      constexpr bool PREFETCH_ACC = !CONV && (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_ERF);
       uint32_t vacc[32];
       if (PREFETCH_ACC) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + chalf * 32), vacc);
 #pragma unroll 1
@@ -1052,18 +1279,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a.y = a.y * p.alpha + bias4.y;
             a.z = a.z * p.alpha + bias4.z;
             a.w = a.w * p.alpha + bias4.w;
-            if (EPI == EPI_BF16_GELU) {
-              if (p.gelu_erf) {   // exact GELU (nn.GELU default: SwinIR's Mlp); warp-uniform branch
-                a.x = 0.5f * a.x * (1.0f + erff(a.x * 0.70710678118654752f));
-                a.y = 0.5f * a.y * (1.0f + erff(a.y * 0.70710678118654752f));
-                a.z = 0.5f * a.z * (1.0f + erff(a.z * 0.70710678118654752f));
-                a.w = 0.5f * a.w * (1.0f + erff(a.w * 0.70710678118654752f));
-              } else {            // tanh approximation (PixArt's Mlp, approximate="tanh")
-                a.x = gelu_tanh_fast(a.x);
-                a.y = gelu_tanh_fast(a.y);
-                a.z = gelu_tanh_fast(a.z);
-                a.w = gelu_tanh_fast(a.w);
-              }
+            if constexpr (EPI == EPI_BF16_GELU_ERF) {   // exact GELU (nn.GELU default: SwinIR's Mlp)
+              a.x = 0.5f * a.x * (1.0f + erff(a.x * 0.70710678118654752f));
+              a.y = 0.5f * a.y * (1.0f + erff(a.y * 0.70710678118654752f));
+              a.z = 0.5f * a.z * (1.0f + erff(a.z * 0.70710678118654752f));
+              a.w = 0.5f * a.w * (1.0f + erff(a.w * 0.70710678118654752f));
+            } else if constexpr (EPI == EPI_BF16_GELU) {   // tanh approximation (PixArt's Mlp, approximate="tanh")
+              a.x = gelu_tanh_fast(a.x);
+              a.y = gelu_tanh_fast(a.y);
+              a.z = gelu_tanh_fast(a.z);
+              a.w = gelu_tanh_fast(a.w);
             }
             if (EPI == EPI_F32) {
               const long o = (long)b * p.stride_of + row_off[i] * p.ldo_f + col;
@@ -1243,6 +1468,7 @@ static int num_sms() { return device_num_sms(); }
 
 static constexpr int RED_ADD_DEFAULT = 0;   // measured on B200 (interleaved A/B, 1024^2 step): cross-proj / after_proj 23.2 -> 22.8 us, fc2 47.1 -> 47.4 us, step 21.6 vs 21.5-21.8 ms: a wash -> off
 static constexpr int ROW_PATH_DEFAULT = 1;   // measured on B200: plain bf16 gains (qkv-like 29.3 -> 27.4 us), GELU and fp32-residual lose (34.9 -> 40.8, 18.1 -> 22.6 us)
+static constexpr int DIRECT_DEFAULT = 8;   // direct row-owner epilogue (see gemm_launch), measured on B200 against the incumbents (isolated launches, M 4096 / 25600 / 1024): qkv scatter 30.4 -> 29.4, 160.8 -> 154.4, 15.7 -> 13.1 us: on; plain bf16 a tie (13.7 vs 13.6, 54.2 vs 55.7), GELU 31.9 vs 32.3, fp32-residual 16.2 -> 19.5 us (one 32-byte L2 request per thread and sector: 3x the write requests of the coalesced stores): off
 static long long* g_gemm_trace = nullptr;
 static int g_gemm_trace_slots = 1, g_gemm_trace_next = 0;
 void gemm_set_trace(long long* device_buf, int slots) {
@@ -1316,7 +1542,9 @@ static int launch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, con
                       const CUtensorMap& tf, const GemmDev& p, cudaStream_t s) {
   switch (epi) {
     case EPI_BF16: return launch_inst<BN, EPI_BF16, CONV, CG>(ta, tw, to, tr, tf, p, s);
-    case EPI_BF16_GELU: return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, to, tr, tf, p, s);
+    case EPI_BF16_GELU:   // the exact (erf) variant is its own instantiation: inlined erff bloats the unrolled epilogue code
+      if (p.gelu_erf) return launch_inst<BN, EPI_BF16_GELU_ERF, CONV, CG>(ta, tw, to, tr, tf, p, s);
+      return launch_inst<BN, EPI_BF16_GELU, CONV, CG>(ta, tw, to, tr, tf, p, s);
     case EPI_F32: return launch_inst<BN, EPI_F32, CONV, CG>(ta, tw, to, tr, tf, p, s);
     case EPI_QKV:
       if (!CONV) return launch_inst<BN, EPI_QKV, false, CG>(ta, tw, to, tr, tf, p, s);
@@ -1592,6 +1820,28 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     }
   }
   IR_REQUIRE(a.epi != EPI_ATTN || p.row_path, "gemm: EPI_ATTN needs the row-owner epilogue");
+  // direct row-owner epilogue (TMEM -> registers -> 256-bit global stores, no shared-memory staging): whole 32-column chunks
+  // and 32-byte aligned rows. Bits of the mask: 1 plain bf16, 2 GELU, 4 fp32-residual, 8 qkv scatter (IR_GEMM_DIRECT: A/B
+  // switch of debug builds)
+  if (!a.conv && a.epi != EPI_ATTN && !a.resid_bf16 && !a.gn_partial && !p.red_add && a.N % 32 == 0) {
+    static const int direct_mask = [] {
+      const char* e = debug_env("IR_GEMM_DIRECT");
+      return e ? atoi(e) : DIRECT_DEFAULT;
+    }();
+    auto al = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
+    const int bit = a.epi == EPI_BF16 ? 1 : a.epi == EPI_BF16_GELU ? 2 : a.epi == EPI_F32 ? 4 : 8;
+    bool ok = (direct_mask & bit) != 0 && (!a.bias || (al(a.bias, 16) && a.stride_bias % 4 == 0));
+    const bool ob_ok = al(a.out_bf16, 32) && a.ldo_b % 16 == 0 && (a.batch == 1 || a.stride_ob % 16 == 0);
+    if (a.epi == EPI_QKV) {
+      ok = ok && al(a.q_heads, 16) && al(a.k_heads, 16) && a.qkv_hd % 8 == 0;
+    } else if (a.epi == EPI_F32) {
+      ok = ok && al(a.out_f32, 32) && al(a.resid_f32, 32) && a.ldo_f % 8 == 0 && (a.batch == 1 || a.stride_of % 8 == 0) &&
+           (!a.out_bf16 || ob_ok) && (!a.gate || al(a.gate, 16));
+    } else {
+      ok = ok && ob_ok;
+    }
+    if (ok) p.row_path = 2;
+  }
 
   if (a.conv) {
     if (tc.cg == 2) {

@@ -11,6 +11,7 @@ enum GemmEpilogue {
   EPI_QKV = 3,        // attn.qkv projection scattered head-major for the tcgen05 attention kernel:
                       //   q, k -> [B][H][T][hd] bf16, v -> transposed [B][H][hd][Tp] bf16 (acc + bias)
   EPI_ATTN = 4,       // the passes of a materialised single-head attention (VAE AttnBlock, model.py:181-205), see att_mode
+  EPI_BF16_GELU_ERF = 5,  // internal: the instantiation EPI_BF16_GELU + GemmArgs::gelu_erf is launched as (callers pass EPI_BF16_GELU)
 };
 
 // C[b][m][n] = sum_k A[b][m][k] * W[b][n][k]   (both operands K-major bf16, fp32 accumulation in TMEM).

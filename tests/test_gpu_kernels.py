@@ -28,7 +28,9 @@ def _close(got, ref, tol):
 
 
 @pytest.mark.parametrize("cfg", CFGS)
-@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1152, 1152), (130, 3456, 192)])
+# N % 32 == 0: whole-chunk epilogues; N = 136 (row stride a multiple of 16 bytes): the TMA-store row-owner epilogue with an N
+# tail; N = 132: neither TMA-storable nor chunk-aligned -> the transposing epilogue with an N tail
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 1152, 1152), (130, 3456, 192), (200, 136, 192), (200, 132, 64)])
 def test_gemm_bf16_epilogues(ctx, cfg, M, N, K):
     _lib, L, dev = ctx
     g = torch.Generator().manual_seed(M + N + K + cfg)
@@ -236,6 +238,31 @@ def test_qkv_heads_and_tcgen05_attention(ctx, B, T):
     torch.cuda.synchronize()
     sref = F.scaled_dot_product_attention(qh.float(), kh.float(), vt[..., :T].float().transpose(2, 3))
     _close(out, sref.permute(0, 2, 1, 3).reshape(M, D), 1e-2)
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("heads,hd", [(16, 72), (8, 36)])
+def test_qkv_heads_scatter_every_tile_config(ctx, cfg, heads, hd):
+    """Head-major q / k / transposed-v scatter for every tile configuration. head_dim 72 takes the direct row-owner epilogue
+    (TMEM -> registers -> global), head_dim 36 (not a multiple of 8: a 16-byte piece would straddle heads) the transposing
+    one; ragged sample length, so that the 32 rows of a warp straddle two samples."""
+    _lib, L, dev = ctx
+    B, T = 2, 200
+    D, M, Tp = heads * hd, B * T, (T + 7) // 8 * 8
+    g = torch.Generator().manual_seed(cfg + hd)
+    A = (torch.randn(M, D, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(3 * D, D, generator=g) * 0.03).to(dev).bfloat16()
+    bias = (torch.randn(3 * D, generator=g) * 0.1).to(dev)
+    qh = torch.zeros(B, heads, T, hd, device=dev, dtype=torch.bfloat16)
+    kh = torch.zeros_like(qh)
+    vt = torch.zeros(B, heads, hd, Tp, device=dev, dtype=torch.bfloat16)
+    _lib.check(L.ir_gemm_qkv_heads(A.data_ptr(), W.data_ptr(), bias.data_ptr(), M, D, T, Tp, heads, hd, qh.data_ptr(),
+                                   kh.data_ptr(), vt.data_ptr(), cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = (A.float() @ W.float().t() + bias).view(B, T, 3, heads, hd)
+    _close(qh, ref[:, :, 0].permute(0, 2, 1, 3), 1e-2)
+    _close(kh, ref[:, :, 1].permute(0, 2, 1, 3), 1e-2)
+    _close(vt[..., :T], ref[:, :, 2].permute(0, 2, 3, 1), 1e-2)
 
 
 @pytest.mark.parametrize("B,T,qscale", [(1, 4096, 30.0), (1, 1000, 4.0), (2, 1536, 1.0), (1, 130, 8.0)])
