@@ -862,6 +862,231 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if constexpr (!CONV && EPI == EPI_F32) {
+      if (p.row_path == 3) {
+        // -------- fp32-residual epilogue, lean transposing form: x += gate * (alpha * acc + bias) in place on the fp32 stream
+        // (PixArtMS.py:71-79) with an optional bf16 copy. Same data movement as the generic transposing epilogue below
+        // (TMEM -> registers -> per-warp staging -> coalesced 128-byte row segments), but nothing is recomputed inside the
+        // row loop: the ncu instruction mix of the generic code on the proj GEMM (M 4096, N = K = 1152) was 18.6 k warp
+        // instructions per 128 x 128 tile against ~2 k of arithmetic and memory instructions -- per-row 64-bit index
+        // arithmetic, null-pointer and tail predicates, register copies of the prefetched residual -- i.e. the epilogue was
+        // bound by issue slots, not by the 160 KB it moves. Here a lane keeps eight 32-bit element offsets and a validity
+        // mask per tile, the residual of the next chunk ping-pongs between two register sets, and the per-tile conditions
+        // (bias, gate, per-row gates of a tile that straddles two samples, bf16 copy) are warp-uniform branches around whole
+        // chunk bodies. Host-checked: N % 32 == 0, 16-byte aligned rows, one leading dimension for the fp32 stream and its
+        // bf16 copy, offsets below 2^31.
+        row_path_done = true;
+        constexpr int NCH = (BN / 32 + CSTEP - 1) / CSTEP;   // chunks per warp and tile
+        const uint32_t lane_tmem = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool has_resid = p.resid_f32 != nullptr;
+        const bool has_copy = p.out_bf16 != nullptr;
+        int it = 0;
+        for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
+          const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+          const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
+          const int b = mb / p.m_units;
+          const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          // rows this lane touches after the transpose: q * 32 + i * 4 + rsub, i = 0..7
+          const int gm0 = m_blk * BM + q * 32 + rsub;
+          uint32_t off[8];
+          uint32_t valid = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int gm = gm0 + 4 * i;
+            off[i] = (uint32_t)gm * (uint32_t)p.ldo_f + (uint32_t)(n_blk * BN + col4);
+            valid |= (gm < p.M ? 1u : 0u) << i;
+          }
+          const float* rbase = has_resid ? p.resid_f32 + (long)b * p.stride_of : nullptr;
+          float* fbase = p.out_f32 + (long)b * p.stride_of;
+          bf16* bbase = has_copy ? p.out_bf16 + (long)b * p.stride_ob : nullptr;
+          const float* biasp = p.bias ? p.bias + (long)b * p.stride_bias + n_blk * BN + col4 : nullptr;
+          // gate: one row of the table per sample; a tile whose rows belong to one sample reads it once per chunk
+          const int row_lo = m_blk * BM, row_hi = min(row_lo + BM, p.M) - 1;
+          const int g_lo = row_lo / p.rows_per_gate;
+          const bool gate_uniform = p.gate == nullptr || row_hi < row_lo || g_lo == row_hi / p.rows_per_gate;
+          const float* gatep = p.gate ? p.gate + (long)g_lo * p.gate_ld + n_blk * BN + col4 : nullptr;
+          auto ccol = [&](int k) { return (chalf + k * CSTEP) * 32; };   // column offset of this warp's k-th chunk in the tile
+          auto cok = [&](int k) { return n_blk * BN + ccol(k) < p.N; };
+          auto rload = [&](float4 (&r)[8], int k) {
+            if (has_resid && cok(k)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                r[i] = (valid >> i & 1u) ? *reinterpret_cast<const float4*>(rbase + off[i] + ccol(k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          auto chunk = [&](const float4 (&r)[8], int k, bool last) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_tmem + (uint32_t)(buf * BN + ccol(k)), v);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gate4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            const bool ok = cok(k);
+            if (ok) {
+              if (biasp) bias4 = __ldg(reinterpret_cast<const float4*>(biasp + ccol(k)));
+              if (gatep) gate4 = __ldg(reinterpret_cast<const float4*>(gatep + ccol(k)));
+            }
+            tmem_ld_wait();
+            if (last) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_f4(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u,
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3])));
+            __syncwarp();
+            if (ok) {
+              float4 av[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = lds_f4(stg_s + (uint32_t)((i * 4 + rsub) * STG_LD + col4) * 4u);
+              // premultiplied: x = r + (alpha * gate) * acc + gate * bias
+              const float4 ag = make_float4(p.alpha * gate4.x, p.alpha * gate4.y, p.alpha * gate4.z, p.alpha * gate4.w);
+              const float4 gb = make_float4(gate4.x * bias4.x, gate4.y * bias4.y, gate4.z * bias4.z, gate4.w * bias4.w);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (!(valid >> i & 1u)) continue;
+                float4 a;
+                if (gate_uniform) {
+                  a.x = fmaf(av[i].x, ag.x, gb.x) + r[i].x;
+                  a.y = fmaf(av[i].y, ag.y, gb.y) + r[i].y;
+                  a.z = fmaf(av[i].z, ag.z, gb.z) + r[i].z;
+                  a.w = fmaf(av[i].w, ag.w, gb.w) + r[i].w;
+                } else {   // the tile straddles two samples: this row's own gate
+                  const int gm = gm0 + 4 * i;
+                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + (long)(gm / p.rows_per_gate) * p.gate_ld +
+                                                                          n_blk * BN + col4 + ccol(k)));
+                  a.x = fmaf(fmaf(av[i].x, p.alpha, bias4.x), g4.x, r[i].x);
+                  a.y = fmaf(fmaf(av[i].y, p.alpha, bias4.y), g4.y, r[i].y);
+                  a.z = fmaf(fmaf(av[i].z, p.alpha, bias4.z), g4.z, r[i].z);
+                  a.w = fmaf(fmaf(av[i].w, p.alpha, bias4.w), g4.w, r[i].w);
+                }
+                *reinterpret_cast<float4*>(fbase + off[i] + ccol(k)) = a;
+                if (has_copy)
+                  *reinterpret_cast<uint2*>(bbase + off[i] + ccol(k)) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              }
+            }
+            __syncwarp();   // the staging area is rewritten by the next chunk
+          };
+          float4 ra[8], rb[8];
+          rload(ra, 0);   // requested before the wait for the accumulator: its latency runs under the tile's own MMAs
+          mbar_wait(&tfull_bar[buf], use & 1);
+          tc_fence_after();
+          if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+#pragma unroll
+          for (int k = 0; k < NCH; k += 2) {
+            if (k + 1 < NCH) rload(rb, k + 1);
+            chunk(ra, k, k + 1 >= NCH);
+            if (k + 1 < NCH) {
+              if (k + 2 < NCH) rload(ra, k + 2);
+              chunk(rb, k + 1, k + 2 >= NCH);
+            }
+          }
+          if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));
+        }
+      }
+    }
+    if constexpr (!CONV && (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_GELU_ERF)) {
+      if (p.row_path == 3) {
+        // -------- bf16 / GELU epilogue, lean transposing form (see the fp32-residual one above): out = act(alpha * acc + bias).
+        // The accumulator chunk of the next iteration is in flight (second register set) while the current one is staged,
+        // transposed and stored; per-tile offsets and validity mask instead of per-row index arithmetic.
+        row_path_done = true;
+        constexpr int NCH = (BN / 32 + CSTEP - 1) / CSTEP;
+        const uint32_t lane_tmem = tmem_base + ((uint32_t)(q * 32) << 16);
+        int it = 0;
+        for (int tile = unit0; tile < p.num_tiles; tile += unit_stride, ++it) {
+          const int n_blk = p.raster_n ? tile % p.n_blocks : tile / mb_total;
+          const int mb = p.raster_n ? tile / p.n_blocks : tile - n_blk * mb_total;
+          const int b = mb / p.m_units;
+          const int m_blk = (mb - b * p.m_units) * CG + (int)cta_rank;
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          const int gm0 = m_blk * BM + q * 32 + rsub;
+          uint32_t off[8];
+          uint32_t valid = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int gm = gm0 + 4 * i;
+            off[i] = (uint32_t)gm * (uint32_t)p.ldo_b + (uint32_t)(n_blk * BN + col4);
+            valid |= (gm < p.M ? 1u : 0u) << i;
+          }
+          bf16* bbase = p.out_bf16 + (long)b * p.stride_ob;
+          const float* biasp = p.bias ? p.bias + (long)b * p.stride_bias + n_blk * BN + col4 : nullptr;
+          auto ccol = [&](int k) { return (chalf + k * CSTEP) * 32; };
+          auto cok = [&](int k) { return n_blk * BN + ccol(k) < p.N; };
+          auto tload = [&](uint32_t (&v)[32], int k) { tmem_ld_32x32(lane_tmem + (uint32_t)(buf * BN + ccol(k)), v); };
+          auto release = [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tempty_bar[buf], 0); else mbar_arrive(&tempty_bar[buf]);
+            }
+          };
+          auto chunk = [&](const uint32_t (&v)[32], int k) {
+            const bool ok = cok(k);
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && biasp) bias4 = __ldg(reinterpret_cast<const float4*>(biasp + ccol(k)));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_f4(stg_s + (uint32_t)(lane * STG_LD + 4 * j) * 4u,
+                     make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3])));
+            __syncwarp();
+            if (ok) {
+              float4 av[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = lds_f4(stg_s + (uint32_t)((i * 4 + rsub) * STG_LD + col4) * 4u);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (!(valid >> i & 1u)) continue;
+                float4 a;
+                a.x = fmaf(av[i].x, p.alpha, bias4.x);
+                a.y = fmaf(av[i].y, p.alpha, bias4.y);
+                a.z = fmaf(av[i].z, p.alpha, bias4.z);
+                a.w = fmaf(av[i].w, p.alpha, bias4.w);
+                if constexpr (EPI == EPI_BF16_GELU_ERF) {   // exact GELU (nn.GELU default: SwinIR's Mlp)
+                  a.x = 0.5f * a.x * (1.0f + erff(a.x * 0.70710678118654752f));
+                  a.y = 0.5f * a.y * (1.0f + erff(a.y * 0.70710678118654752f));
+                  a.z = 0.5f * a.z * (1.0f + erff(a.z * 0.70710678118654752f));
+                  a.w = 0.5f * a.w * (1.0f + erff(a.w * 0.70710678118654752f));
+                } else if constexpr (EPI == EPI_BF16_GELU) {   // tanh approximation (PixArt's Mlp, approximate="tanh")
+                  a.x = gelu_tanh_fast(a.x);
+                  a.y = gelu_tanh_fast(a.y);
+                  a.z = gelu_tanh_fast(a.z);
+                  a.w = gelu_tanh_fast(a.w);
+                }
+                *reinterpret_cast<uint2*>(bbase + off[i] + ccol(k)) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+              }
+            }
+            __syncwarp();   // the staging area is rewritten by the next chunk
+          };
+          mbar_wait(&tfull_bar[buf], use & 1);
+          tc_fence_after();
+          if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
+          uint32_t va[32], vb[32];
+          tload(va, 0);
+#pragma unroll
+          for (int k = 0; k < NCH; k += 2) {
+            tmem_ld_wait();
+            if (k + 1 < NCH) tload(vb, k + 1); else release();
+            chunk(va, k);
+            if (k + 1 < NCH) {
+              tmem_ld_wait();
+              if (k + 2 < NCH) tload(va, k + 2); else release();
+              chunk(vb, k + 1);
+            }
+          }
+          if (warp == 4) IR_STAMP(12 + (it < 1 ? 0 : 1));
+        }
+      }
+    }
     if constexpr (!CONV && EPI != EPI_QKV) {
       if (p.row_path == 1) {
         // -------- linear GEMMs, row-owner epilogue: a thread owns one output row (its TMEM lane) and 32 consecutive columns
@@ -1841,6 +2066,31 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
       ok = ok && ob_ok;
     }
     if (ok) p.row_path = 2;
+  }
+  // lean transposing fp32-residual epilogue (see the kernel): whole 32-column chunks, 16-byte aligned rows, the bf16 copy on the
+  // stream's own leading dimension, 32-bit element offsets (IR_GEMM_LEAN=0: A/B switch of debug builds)
+  if (!a.conv && a.epi == EPI_F32 && p.row_path != 2 && !p.red_add && a.N % 32 == 0) {
+    static const int lean_on = [] {
+      const char* e = debug_env("IR_GEMM_LEAN");
+      return e ? atoi(e) : 1;
+    }();
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool ok = lean_on && al16(a.out_f32) && al16(a.resid_f32) && a.ldo_f % 4 == 0 && a.stride_of % 4 == 0 &&
+                    (long)a.M * a.ldo_f < (1L << 31) &&
+                    (!a.out_bf16 || (al16(a.out_bf16) && a.ldo_b == a.ldo_f && a.stride_ob % 8 == 0)) &&
+                    (!a.bias || (al16(a.bias) && a.stride_bias % 4 == 0)) && (!a.gate || al16(a.gate));
+    if (ok) p.row_path = 3;
+  }
+  // the same lean form for the GELU epilogue (and for plain bf16 outputs that cannot take the TMA-store path)
+  if (!a.conv && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && p.row_path == 0 && !a.resid_bf16 && !a.gn_partial && a.N % 32 == 0) {
+    static const int lean_on = [] {
+      const char* e = debug_env("IR_GEMM_LEAN_BF16");
+      return e ? atoi(e) : 1;
+    }();
+    auto al = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
+    const bool ok = lean_on && al(a.out_bf16, 8) && a.ldo_b % 4 == 0 && a.stride_ob % 4 == 0 && (long)a.M * a.ldo_b < (1L << 31) &&
+                    (!a.bias || (al(a.bias, 16) && a.stride_bias % 4 == 0));
+    if (ok) p.row_path = 3;
   }
 
   if (a.conv) {

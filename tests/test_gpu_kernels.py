@@ -73,6 +73,17 @@ def test_gemm_f32_gate_residual_inplace_and_batched(ctx, cfg):
                                   _lib.stream_ptr()))
         torch.cuda.synchronize()
         _close(x2, ref2, 2e-3)
+    # samples of 100 rows: every 128-row tile straddles two or three samples (per-row gate rows inside a tile), bf16 copy on
+    T3 = 100
+    gate3 = torch.randn(7, 6 * N, generator=g).to(dev)
+    x3 = torch.randn(700, N, generator=g).to(dev)
+    xb3 = torch.empty(700, N, device=dev, dtype=torch.bfloat16)
+    ref3 = x3 + gate3[:, 2 * N:3 * N].repeat_interleave(T3, 0) * (A[:700].float() @ W.float().t() + bias)
+    _lib.check(L.ir_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), 700, N, K, 1, 0, 0, 0, 2, 1.0, xb3.data_ptr(),
+                              x3.data_ptr(), x3.data_ptr(), gate3.data_ptr() + 2 * N * 4, 6 * N, T3, cfg, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    _close(x3, ref3, 2e-3)
+    _close(xb3, ref3, 1e-2)
     # batched with a shared A operand and per-batch bias (the caption K/V projection of all blocks in one launch)
     nb, Mb = 5, 77
     A2 = (torch.randn(Mb, K, generator=g) * 0.5).to(dev).bfloat16()

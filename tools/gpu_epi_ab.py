@@ -16,6 +16,10 @@ def t(fn, it=30):
 
 
 D, H, hd = 1152, 16, 72
+# clock / allocator warm-up: the first timed case of a fresh process otherwise reads 2-4x high
+_w = torch.randn(4096, 4096, device=dev).bfloat16()
+for _ in range(200): _w @ _w
+torch.cuda.synchronize(); del _w
 for M, T in ((4096, 4096), (1024, 1024), (25600, 1024)):
     Tp = (T + 7) // 8 * 8
     A = torch.randn(M, D, device=dev).bfloat16(); A4 = torch.randn(M, 4 * D, device=dev).bfloat16()
