@@ -104,6 +104,7 @@ struct GemmDev {
   float* att_out;
   int red_add;        // EPI_F32 row-owner epilogue, in-place update without a bf16 copy: x += gate * (acc + bias) leaves as a
                       // TMA reduce-add store (the residual is never read by the SM)
+  int lean_depth2;    // lean fp32-residual epilogue: residual rows of the first two chunks requested before the accumulator wait
   int row_path;       // linear GEMM: row-owner epilogue with TMA-store boxes (host-checked alignment), else the transposing one
   long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
 };
@@ -962,10 +963,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   const int gm = gm0 + 4 * i;
                   const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + (long)(gm / p.rows_per_gate) * p.gate_ld +
                                                                           n_blk * BN + col4 + ccol(k)));
-                  a.x = fmaf(fmaf(av[i].x, p.alpha, bias4.x), g4.x, r[i].x);
-                  a.y = fmaf(fmaf(av[i].y, p.alpha, bias4.y), g4.y, r[i].y);
-                  a.z = fmaf(fmaf(av[i].z, p.alpha, bias4.z), g4.z, r[i].z);
-                  a.w = fmaf(fmaf(av[i].w, p.alpha, bias4.w), g4.w, r[i].w);
+                  // the same arithmetic as the uniform case (a row's result must not depend on which tile it lands in: results
+                  // are bit-identical for every batch composition / sharding)
+                  a.x = fmaf(av[i].x, p.alpha * g4.x, g4.x * bias4.x) + r[i].x;
+                  a.y = fmaf(av[i].y, p.alpha * g4.y, g4.y * bias4.y) + r[i].y;
+                  a.z = fmaf(av[i].z, p.alpha * g4.z, g4.z * bias4.z) + r[i].z;
+                  a.w = fmaf(av[i].w, p.alpha * g4.w, g4.w * bias4.w) + r[i].w;
                 }
                 *reinterpret_cast<float4*>(fbase + off[i] + ccol(k)) = a;
                 if (has_copy)
@@ -975,13 +978,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();   // the staging area is rewritten by the next chunk
           };
           float4 ra[8], rb[8];
-          rload(ra, 0);   // requested before the wait for the accumulator: its latency runs under the tile's own MMAs
+          // the residual rows of the first TWO chunks are requested before the wait for the accumulator: their latency (the
+          // stream may have left the L2 since the previous block touched it) runs under the tile's own MMAs, and the second
+          // chunk does not wait out a DRAM round trip behind the short first one
+          rload(ra, 0);
+          if (NCH > 1 && p.lean_depth2) rload(rb, 1);
           mbar_wait(&tfull_bar[buf], use & 1);
           tc_fence_after();
           if (warp == 4) IR_STAMP(10 + (it < 1 ? 0 : 1));
 #pragma unroll
           for (int k = 0; k < NCH; k += 2) {
-            if (k + 1 < NCH) rload(rb, k + 1);
+            if (k + 1 < NCH && !(p.lean_depth2 && k == 0)) rload(rb, k + 1);
             chunk(ra, k, k + 1 >= NCH);
             if (k + 1 < NCH) {
               if (k + 2 < NCH) rload(ra, k + 2);
@@ -2072,8 +2079,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   if (!a.conv && a.epi == EPI_F32 && p.row_path != 2 && !p.red_add && a.N % 32 == 0) {
     static const int lean_on = [] {
       const char* e = debug_env("IR_GEMM_LEAN");
-      return e ? atoi(e) : 1;
+      return e ? atoi(e) : 2;
     }();
+    p.lean_depth2 = lean_on >= 2 ? 1 : 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool ok = lean_on && al16(a.out_f32) && al16(a.resid_f32) && a.ldo_f % 4 == 0 && a.stride_of % 4 == 0 &&
                     (long)a.M * a.ldo_f < (1L << 31) &&

@@ -77,6 +77,7 @@ def test_gemm_f32_gate_residual_inplace_and_batched(ctx, cfg):
     T3 = 100
     gate3 = torch.randn(7, 6 * N, generator=g).to(dev)
     x3 = torch.randn(700, N, generator=g).to(dev)
+    x3_first = x3[200:300].clone()   # sample 2: rows 200..299 straddle the tiles [128, 256) and [256, 384)
     xb3 = torch.empty(700, N, device=dev, dtype=torch.bfloat16)
     ref3 = x3 + gate3[:, 2 * N:3 * N].repeat_interleave(T3, 0) * (A[:700].float() @ W.float().t() + bias)
     _lib.check(L.ir_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr(), 700, N, K, 1, 0, 0, 0, 2, 1.0, xb3.data_ptr(),
@@ -84,6 +85,13 @@ def test_gemm_f32_gate_residual_inplace_and_batched(ctx, cfg):
     torch.cuda.synchronize()
     _close(x3, ref3, 2e-3)
     _close(xb3, ref3, 1e-2)
+    # the same sample alone (one tile, one gate row for the whole tile): bit-identical to its rows inside the batch
+    A3 = A[200:300].contiguous()
+    _lib.check(L.ir_gemm_bf16(A3.data_ptr(), W.data_ptr(), bias.data_ptr(), 100, N, K, 1, 0, 0, 0, 2, 1.0, None,
+                              x3_first.data_ptr(), x3_first.data_ptr(), gate3.data_ptr() + (2 * 6 * N + 2 * N) * 4, 6 * N, T3, cfg,
+                              _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(x3_first, x3[200:300]), "a row's result depends on the batch it was computed in"
     # batched with a shared A operand and per-batch bias (the caption K/V projection of all blocks in one launch)
     nb, Mb = 5, 77
     A2 = (torch.randn(Mb, K, generator=g) * 0.5).to(dev).bfloat16()
