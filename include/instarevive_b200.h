@@ -58,6 +58,9 @@ int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launc
  * folded into M; conv: pixels x Cout x taps*Cin; self-attention: B*heads, T, head_dim) and duration in ms. Call after the
  * work was enqueued and before ir_profile_end; synchronises the device. Returns the record count (only `cap` written). */
 long long ir_profile_records(int* klass, int* M, int* N, int* K, float* ms, long long cap);
+/* Floor of the event-pair measurement: enqueues n empty kernels, each bracketed like a profiled launch (class 4 of
+ * ir_profile_end: ms / launches = what an event pair adds to a launch's duration on this device). Between begin and end. */
+int ir_profile_calibrate(int n, void* stream);
 
 /* ------------------------------------------------------------------ DiT + ControlNet-Half ---- */
 typedef struct ir_dit ir_dit; /* opaque: packed weights of one (device, model) */

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "ir_profile_begin": (None, []),
     "ir_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "ir_profile_records": (_ll, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_f), _ll]),
+    "ir_profile_calibrate": (_i, [_i, _vp]),
     "ir_dit_create": (_i, [C.POINTER(DitConfig), C.POINTER(_vp)]),
     "ir_dit_destroy": (None, [_vp]),
     "ir_dit_num_params": (_i, [_vp]),

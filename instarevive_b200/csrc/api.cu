@@ -157,6 +157,27 @@ int ir_profile_end(double* ms_by_class, double* flops_by_class, long long* launc
   return IR_OK;
 }
 
+__global__ void profile_empty_kernel() {}
+
+int ir_profile_calibrate(int n, void* stream) {
+  // The floor of the event-pair measurement: n empty one-warp kernels, each between its own pair of events exactly like a
+  // profiled launch. What ir_profile_end then reports for class 4 (ms / launches) is what an event pair adds to a kernel's
+  // duration -- the launch no longer hides behind its predecessor (no programmatic overlap across an event) plus the two
+  // event records -- measured on this device in this process.
+  if (!g_prof_on || n <= 0) {
+    set_last_error("ir_profile_calibrate: call between ir_profile_begin and ir_profile_end with n > 0");
+    return IR_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    prof_before(s);
+    profile_empty_kernel<<<1, 32, 0, s>>>();
+    prof_after(s, PROF_CAL, 0.0);
+  }
+  IR_CUDA_CHECK(cudaGetLastError());
+  return IR_OK;
+}
+
 int ir_dit_create(const ir_dit_config* cfg, ir_dit** out) {
   if (!cfg || !out) {
     set_last_error("ir_dit_create: null argument");

@@ -166,6 +166,14 @@ int dit_create(const DitConfig& cfg, Dit** out) {
   return IR_OK;
 }
 
+static constexpr bool DUAL_HALF_DEFAULT = false;   // measured on B200 (interleaved A/B, 1024^2 step): 21.2-21.4 ms with half-width grids against 20.8-21.1 ms: off
+static bool dual_half_enabled() {
+  static const bool on = [] {
+    const char* e = debug_env("IR_DUAL_HALF");   // A/B switch of debug builds
+    return e ? e[0] != '0' : DUAL_HALF_DEFAULT;
+  }();
+  return on;
+}
 static bool dual_chain_enabled() {
   static const bool on = [] {
     const char* e = debug_env("IR_DIT_SINGLE_STREAM");   // A/B aid (debug builds only)
@@ -326,7 +334,7 @@ __global__ void cond_scalars_kernel(const float* __restrict__ t, const float* __
 
 // one PixArtMSBlock (PixArtMS.py:71-79) on the fp32 stream xs with the scratch of chain `w`, enqueued on stream `s`;
 // bf16_copy (optional) receives bf16(xs) at the end
-static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs& w, cudaStream_t s) {
+static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs& w, cudaStream_t s, int sm_limit = 0) {
   Dit* d = c.d;
   const BlockW& bw = d->blocks[blk];
   const int D = d->cfg.hidden, Dm = D * d->cfg.mlp_ratio, M = c.M, T = c.T;
@@ -342,6 +350,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     g.epi = EPI_QKV; g.bias = bw.b_qkv;
     g.q_heads = w.qh; g.k_heads = w.kh; g.vt_heads = w.vt;
     g.qkv_T = T; g.qkv_Tp = Tp; g.qkv_H = H; g.qkv_hd = hd;
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
     AttnTcArgs a;
     a.q = w.qh; a.k = w.kh; a.vt = w.vt; a.out = w.att; a.ldo = D;
@@ -354,6 +363,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     g.epi = EPI_F32; g.bias = bw.b_proj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
     g.gate = mod + 2 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
     g.out_bf16 = w.xq; g.ldo_b = D;  // bf16(x) feeds the cross-attention query projection
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
   }
   // x = x + cross_attn(x, y, mask)
@@ -361,6 +371,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     GemmArgs g;
     g.A = w.xq; g.lda = D; g.W = bw.q_lin; g.ldw = D; g.M = M; g.N = D; g.K = D;
     g.epi = EPI_BF16; g.bias = bw.b_q; g.out_bf16 = w.qc; g.ldo_b = D;
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
   }
   {
@@ -377,6 +388,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     GemmArgs g;
     g.A = w.att; g.lda = D; g.W = bw.cproj; g.ldw = D; g.M = M; g.N = D; g.K = D;
     g.epi = EPI_F32; g.bias = bw.b_cproj; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
   }
   // x = x + gate_mlp * mlp(modulate(norm2(x)))
@@ -385,6 +397,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     GemmArgs g;
     g.A = w.xn; g.lda = D; g.W = bw.fc1; g.ldw = D; g.M = M; g.N = Dm; g.K = D;
     g.epi = EPI_BF16_GELU; g.bias = bw.b_fc1; g.out_bf16 = w.hm; g.ldo_b = Dm;
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
   }
   {
@@ -393,6 +406,7 @@ static int run_block(Ctx& c, int blk, float* xs, bf16* bf16_copy, const ChainWs&
     g.epi = EPI_F32; g.bias = bw.b_fc2; g.out_f32 = xs; g.resid_f32 = xs; g.ldo_f = D;
     g.gate = mod + 5 * D; g.gate_ld = 6 * D; g.rows_per_gate = T;
     g.out_bf16 = bf16_copy; g.ldo_b = D;
+    g.sm_limit = sm_limit;
     IR_TRY(gemm_launch(g, s));
   }
   return IR_OK;
@@ -543,7 +557,11 @@ static int dit_forward_body(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
     IR_TRY(gemm_launch(g, cs_stream));
     for (int i = 1; i <= ncb; ++i) {
       bf16* cb_i = c.w.cb + (long)(i - 1) * c.M * D;
-      IR_TRY(run_block(c, d->cfg.depth + i - 1, c.w.cs, cb_i, cw, cs_stream));
+      // while both chains have a block in flight (control block i + 1 beside base block i) their persistent GEMMs take half
+      // of the SMs each and run side by side: the fixed costs of the small GEMMs (prologue, pipeline fill, epilogue tail,
+      // launch gap: about half of an N = K = 1152 launch) overlap the other chain's MMAs instead of adding up
+      const int half = (dual && dual_half_enabled()) ? device_num_sms() / 2 / 2 * 2 : 0;
+      IR_TRY(run_block(c, d->cfg.depth + i - 1, c.w.cs, cb_i, cw, cs_stream, i >= 2 ? half : 0));
       if (dual) {
         IR_CUDA_CHECK(cudaEventRecord(d->ev_c[i - 1], cs_stream));
         IR_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_c[i - 1], 0));
@@ -552,8 +570,9 @@ static int dit_forward_body(Dit* d, const DitForwardArgs& a, cudaStream_t s) {
       GemmArgs ga;
       ga.A = cb_i; ga.lda = D; ga.W = d->after_proj[i - 1]; ga.ldw = D; ga.M = c.M; ga.N = D; ga.K = D;
       ga.epi = EPI_F32; ga.bias = d->b_after[i - 1]; ga.out_f32 = c.w.xs; ga.resid_f32 = c.w.xs; ga.ldo_f = D;
+      ga.sm_limit = i < ncb ? half : 0;
       IR_TRY(gemm_launch(ga, s));
-      IR_TRY(run_block(c, i, c.w.xs, nullptr, c.w.ch[0], s));
+      IR_TRY(run_block(c, i, c.w.xs, nullptr, c.w.ch[0], s, i < ncb ? half : 0));
     }
     // the base chain has waited for the last control event: the side stream is joined
     next = ncb + 1;

@@ -104,6 +104,7 @@ struct GemmDev {
   float* att_out;
   int red_add;        // EPI_F32 row-owner epilogue, in-place update without a bf16 copy: x += gate * (acc + bias) leaves as a
                       // TMA reduce-add store (the residual is never read by the SM)
+  int sm_limit;       // host only: SM budget of the launch (0 = all)
   int lean_depth2;    // lean fp32-residual epilogue: residual rows of the first two chunks requested before the accumulator wait
   int row_path;       // linear GEMM: row-owner epilogue with TMA-store boxes (host-checked alignment), else the transposing one
   long long* trace;   // IR_DEBUG builds: %globaltimer stamps of the roles of CTA 0 ([16] int64), else unused
@@ -1728,7 +1729,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   auto kern = gemm_tc_kernel<BN, EPI, CONV, CG>;
   IR_TRY(ensure_smem_optin((const void*)kern, CONV ? SMEM_MAX : Cfg::SMEM_BYTES));
   GemmDev p = p_in;
-  const int slots = num_sms() / CG;
+  const int slots = ((p.sm_limit > 0 && p.sm_limit < num_sms()) ? p.sm_limit : num_sms()) / CG;
   int smem_bytes = Cfg::SMEM_BYTES;
   p.wres = 0;
   p.w_tiles = 0;
@@ -1798,7 +1799,7 @@ struct TileCfg {
 // waves = units / (SMs / CG). Step times measured on B200 with the convergent issue path (tools/gpu_kernel_check.py
 // perf: 8192^3, M4096 x {N4608 K1152, N1152 K4608, N1152 K1152}): per FLOP the 128-wide pair tile costs about what the
 // 256-wide one does, so it wins whenever it quantises better (N = 1152 = 9 x 128).
-static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int k_steps, int forced, bool conv) {
+static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int k_steps, int forced, bool conv, int sm_limit = 0) {
   static int env_cg = -1, env_bn = 0;
   if (env_cg < 0) {
     const char* e = debug_env("IR_GEMM_CFG");  // "cg,bn", e.g. "2,256"
@@ -1809,7 +1810,7 @@ static TileCfg pick_cfg(long m_blocks_total, long m_pairs_total, int N, int k_st
   if (forced == 64 || forced == 128 || forced == 256) return TileCfg{1, forced};
   if ((env_cg == 1 || env_cg == 2) && (env_bn == 64 || env_bn == 128 || env_bn == 256) && !(env_cg == 2 && env_bn == 64))
     return TileCfg{env_cg, env_bn};
-  const int sms = num_sms();
+  const int sms = (sm_limit > 0 && sm_limit < num_sms()) ? sm_limit : num_sms();
   const TileCfg cands[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
   const double unit_cost[5] = {0.415, 0.24, 0.50, 0.285, 0.245};   // us per K-block step
   const double epi_cost[5] = {2.0, 1.0, 2.0, 1.0, 0.6};            // us, last tile's epilogue (not overlapped)
@@ -1970,7 +1971,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
   IR_REQUIRE(a.ldw % 8 == 0 && a.strideW % 8 == 0, "gemm: ldw/strideW must be multiples of 8 elements");
 
   const long m_pairs = (p.m_blocks + 1) / 2;
-  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, (a.conv && !p.s2) ? p.ntap * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0);
+  TileCfg tc = pick_cfg(m_blocks_total, m_pairs * p.batch, a.N, (a.conv && !p.s2) ? p.ntap * p.k_blocks : p.k_blocks, a.force_bn, a.conv != 0, a.sm_limit);
+  p.sm_limit = a.sm_limit;
   if (a.conv && tc.cg == 1 && tc.bn == 256) tc.bn = 128;
   const int bn = tc.bn;
   p.m_units = tc.cg == 2 ? (int)m_pairs : p.m_blocks;

@@ -85,6 +85,8 @@ struct GemmArgs {
   // fused GroupNorm statistics of a conv: partial slot = img * gn_slots_img + gn_slot_off + tile (0 = tiles per image)
   int gn_slot_off = 0, gn_slots_img = 0;
 
+  int sm_limit = 0;  // 0 = all SMs; otherwise the persistent grid uses at most this many SMs (two half-width GEMMs of independent
+                     // streams then run side by side instead of one after the other)
   int force_bn = 0;  // 0 = heuristic; 64 / 128 / 256 = single-CTA tile width; cg*1000 + bn forces (cta_group, width)
 };
 
@@ -127,7 +129,7 @@ void count_launch(int n = 1);
 long long launch_count_value();
 
 // Optional per-launch timing (bench.py roofline pass): CUDA events around the launches of one kernel class.
-enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_XATTN = 3, PROF_NUM = 8 };   // ATTN: tcgen05 self-attention; XATTN: var-len cross-attention
+enum ProfClass { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN = 2, PROF_XATTN = 3, PROF_CAL = 4, PROF_NUM = 8 };   // ATTN: tcgen05 self-attention; XATTN: var-len cross-attention; CAL: empty kernels of ir_profile_calibrate
 bool prof_enabled();
 void prof_before(cudaStream_t s);
 void prof_after(cudaStream_t s, int klass, double flops, int M = 0, int N = 0, int K = 0);
