@@ -501,7 +501,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> global
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global memory
+    // Which code serves which launch (the host picks; p.row_path: 0 generic, 1 TMA-box row-owner, 2 direct row-owner, 3 lean
+    // transposing). Every form computes the same per-element arithmetic in fp32 from the same accumulator, so a result never
+    // depends on the tile configuration or the batch it was computed in.
+    //   conv, bf16 output                pixel-owner epilogue with TMA-store boxes, fused residual / GroupNorm partials
+    //   qkv head scatter (EPI_QKV)       direct row-owner (2): TMEM -> registers -> global, no shared memory; generic (0) when
+    //                                    head_dim % 8 != 0 or the outputs are not 16-byte aligned
+    //   plain bf16 (q_linear, caption)   TMA-box row-owner (1); lean (3) / generic (0) when the output cannot be a TMA box
+    //   GELU (fc1), fp32 residual        lean transposing (3): coalesced 128-byte row segments through a per-warp staging
+    //   (proj, cross-proj, fc2, zero-    tile, per-tile offsets and masks; generic (0) for N % 32 != 0, misaligned rows,
+    //   linears)                         a bf16 copy on another leading dimension
+    //   bf16 + residual / GroupNorm      generic transposing (0): the VAE's 1x1 convs as GEMMs, conv instantiations other
+    //   partials, fp32 conv outputs      than bf16
+    //   EPI_ATTN (VAE mid-attention)     TMA-box row-owner (1) only
     constexpr int EW = Cfg::EW;
     constexpr int CSTEP = EW / 4;           // warps per TMEM lane quarter = chunk interleave
     const int q = warp & 3;                 // TMEM lane quarter this warp may access: lanes [32q, 32q+32)
@@ -913,8 +926,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float* biasp = p.bias ? p.bias + (long)b * p.stride_bias + n_blk * BN + col4 : nullptr;
           // gate: one row of the table per sample; a tile whose rows belong to one sample reads it once per chunk
           const int row_lo = m_blk * BM, row_hi = min(row_lo + BM, p.M) - 1;
-          const int g_lo = row_lo / p.rows_per_gate;
-          const bool gate_uniform = p.gate == nullptr || row_hi < row_lo || g_lo == row_hi / p.rows_per_gate;
+          const bool any_rows = row_lo < p.M;   // the odd tail of a CTA pair owns no rows: it reads no gate row either
+          const int g_lo = any_rows ? row_lo / p.rows_per_gate : 0;
+          const bool gate_uniform = p.gate == nullptr || !any_rows || g_lo == row_hi / p.rows_per_gate;
           const float* gatep = p.gate ? p.gate + (long)g_lo * p.gate_ld + n_blk * BN + col4 : nullptr;
           auto ccol = [&](int k) { return (chalf + k * CSTEP) * 32; };   // column offset of this warp's k-th chunk in the tile
           auto cok = [&](int k) { return n_blk * BN + ccol(k) < p.N; };
